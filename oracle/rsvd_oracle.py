@@ -1,0 +1,286 @@
+"""TEST INFRASTRUCTURE (oracle) -- CPU restatement of the reference's rSVD hot path.  NOT product code.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs (``cpu_baseline`` / ``--impl reference``)
+may import this module.  The product package ``rsvd_kamaneh_raganato_terrana_b200`` never does.
+
+What is restated (reference file:line, relative to /root/reference):
+
+* ``intermediate_step``  src/rSVD.cpp:57-70   (range finder with q power iterations, QR after every product)
+* ``rsvd``               src/rSVD.cpp:72-133  (B = Q^T A, small SVD dispatch, U = Q*Utilde); Omega is an ARGUMENT
+                                               here (the reference draws it from std::random_device, :26-28)
+* small SVD back-ends    include/SVD_class.hpp:101-180 (Jacobi), :224-333 (ParallelJacobi), :184-219 + src/PM.cpp
+                         (Power) -- the loops live in oracle/oracle_c.c
+* Givens QR              src/QR.cpp:12-80, manualMatrixMultiply src/matrixOperations.cpp:7-28 -- oracle_c.c
+
+Third-party arithmetic: the reference calls Eigen (un-vendored, un-pinned: Makefile:2 ``-I ${mkEigenInc}``) for the dense
+products and ``Eigen::HouseholderQR``.  Eigen is absent from this image.  Its published algorithm (unblocked/blocked
+Householder QR with beta = -sign(x0)*||x||, identical to LAPACK dlarfg/dgeqrf/dorgqr) is restated through
+``scipy.linalg.qr(mode="economic")`` for large inputs and ``oc_householder_qr`` (oracle_c.c) for small ones; both give the
+same Q, R up to rounding.  Products go through numpy (OpenBLAS dgemm).
+
+Pin status: the reference holds NO golden vectors for this path.  This oracle is pinned instead against
+(1) outputs of the reference's own first-party sources compiled here over an Eigen/MPI stand-in (oracle/_ref, built by
+oracle/Makefile; compared in tests/test_oracle_vs_ref.py and frozen as tests/golden/*.npz by
+tests/golden/make_golden.py), and (2) the mathematical known answers of BASELINE.md section 3.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import scipy.linalg
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+JACOBI, POWER, PARALLEL_JACOBI = 0, 1, 2   # enum class SVDMethod, include/SVD_class.hpp:28-32
+
+
+def build(force: bool = False) -> Path:
+    """Compile oracle_c.c (and, when /root/reference is present, oracle/_ref) with the committed Makefile."""
+    so = _HERE / "_build" / "liboracle_c.so"
+    src = _HERE / "oracle_c.c"
+    if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "oracle_c"], check=True, capture_output=True)
+    ref_so = _HERE / "_ref" / "libref_rsvd.so"
+    if Path("/root/reference/src").is_dir() and (force or not ref_so.exists()):
+        subprocess.run(["make", "-C", str(_HERE), "ref"], check=True, capture_output=True)
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(str(build()))
+        _LIB.oc_jacobi_svd.restype = ctypes.c_long
+        _LIB.oc_parallel_jacobi_svd.restype = ctypes.c_long
+        _LIB.oc_power_svd.restype = ctypes.c_long
+    return _LIB
+
+
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _f(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Householder QR (Eigen::HouseholderQR semantics)
+# ---------------------------------------------------------------------------------------------------------------
+def householder_qr(Y, small_limit: int = 200_000):
+    """Return (Q_thin, R) with Q_thin = householderQ() * Identity(rows, cols)  (src/rSVD.cpp:60-61)."""
+    Y = _f(Y)
+    m, n = Y.shape
+    if m * n <= small_limit:
+        F = Y.copy(order="F")
+        k = min(m, n)
+        tau = np.zeros(k)
+        _lib().oc_householder_qr(_p(F), ctypes.c_long(m), ctypes.c_long(n), _p(tau))
+        Q = np.asfortranarray(np.eye(m, n))
+        _lib().oc_householder_apply_q(_p(F), ctypes.c_long(m), ctypes.c_long(k), _p(tau), _p(Q), ctypes.c_long(n))
+        return Q, np.triu(F[:k, :])
+    Q, R = scipy.linalg.qr(Y, mode="economic", overwrite_a=False, check_finite=False)
+    return _f(Q), R
+
+
+def intermediate_step(A, Omega, l: int, q: int):
+    """src/rSVD.cpp:57-70.  Returns Q (m x l)."""
+    A = np.asarray(A, dtype=np.float64)
+    Y = A @ Omega                               # :59
+    Q, _ = householder_qr(Y)                    # :60-61
+    for _ in range(q):                          # :62
+        Y = A.T @ Q                             # :63
+        Q, _ = householder_qr(Y)                # :64-65
+        Y = A @ Q                               # :66
+        Q, _ = householder_qr(Y)                # :67-68
+    return Q[:, :l]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Small SVD back-ends (SVD<method>::compute)
+# ---------------------------------------------------------------------------------------------------------------
+def svd_jacobi(B):
+    """include/SVD_class.hpp:101-180.  Returns (U m x k, S k, V n x k, info)."""
+    B = _f(B); m, n = B.shape; k = min(m, n)
+    U = np.zeros((m, k), order="F"); S = np.zeros(k); V = np.zeros((n, k), order="F"); rot = ctypes.c_long(0)
+    sweeps = _lib().oc_jacobi_svd(_p(B), ctypes.c_long(m), ctypes.c_long(n), _p(U), _p(S), _p(V), ctypes.byref(rot))
+    return U, S, V, {"sweeps": int(sweeps), "rotations": int(rot.value)}
+
+
+def svd_parallel_jacobi(B):
+    """include/SVD_class.hpp:224-333."""
+    B = _f(B); m, n = B.shape; k = min(m, n)
+    U = np.zeros((m, k), order="F"); S = np.zeros(k); V = np.zeros((n, k), order="F"); rot = ctypes.c_long(0)
+    passes = _lib().oc_parallel_jacobi_svd(_p(B), ctypes.c_long(m), ctypes.c_long(n), _p(U), _p(S), _p(V), ctypes.byref(rot))
+    return U, S, V, {"passes": int(passes), "rotations": int(rot.value)}
+
+
+def svd_power(B, r: int = 0, seed: int = 0):
+    """include/SVD_class.hpp:184-219 + src/PM.cpp:4-81.  Start vectors come from a seeded generator (the reference uses
+    std::random_device).  Returns (U m x m [or m x found on early exit], S, V n x n with singular vectors in ROWS)."""
+    B = _f(B); m, n = B.shape; k = min(m, n); dim = r if r else k
+    starts = _f(np.random.default_rng(seed).standard_normal((n, dim)))
+    U = np.zeros((m, m), order="F"); S = np.zeros(k); V = np.zeros((n, n), order="F")
+    found = int(_lib().oc_power_svd(_p(B), ctypes.c_long(m), ctypes.c_long(n), ctypes.c_int(r), _p(starts), _p(U), _p(S), _p(V)))
+    if found < dim:    # conservativeResize on early exit, :198-209
+        if found == 0:
+            return np.zeros((m, 1), order="F"), np.zeros(1), np.zeros((n, 1), order="F"), {"found": 0}
+        return _f(U[:, :found]), S[:found].copy(), _f(V[:, :found]), {"found": found}
+    return U, S, V, {"found": found}
+
+
+def pm_iterations(ncols: int) -> int:
+    """src/PM.cpp:25-28."""
+    return int(_lib().oc_pm_iterations(ctypes.c_long(ncols)))
+
+
+def rsvd(A, Omega, l: int, q: int = 2, method: int = JACOBI, seed: int = 0):
+    """src/rSVD.cpp:72-133 with Omega supplied.  Returns (U, S, V) with the reference's output shapes."""
+    A = np.asarray(A, dtype=np.float64)
+    Q = intermediate_step(A, Omega, l, q)       # :84-85
+    B = Q.T @ A                                 # :89
+    if method == JACOBI:
+        Ut, S, V, _ = svd_jacobi(B)
+    elif method == PARALLEL_JACOBI:
+        Ut, S, V, _ = svd_parallel_jacobi(B)
+    elif method == POWER:
+        Ut, S, V, _ = svd_power(B, 0, seed)
+    else:
+        raise ValueError("Unsupported SVD method")   # std::invalid_argument, :122-123
+    return Q @ Ut, S, V                          # :128
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Givens QR / naive GEMM (API-surface helpers)
+# ---------------------------------------------------------------------------------------------------------------
+def givens_qr(A, reduced: bool = True):
+    """src/QR.cpp:22-80."""
+    A = _f(A); m, n = A.shape
+    Q = np.zeros((m, m), order="F"); R = np.zeros((m, n), order="F")
+    _lib().oc_givens_qr_full(_p(A), ctypes.c_long(m), ctypes.c_long(n), _p(Q), _p(R))
+    if reduced:
+        return _f(Q[:, :n]), _f(R[:n, :])       # :78-79
+    return Q, R
+
+
+def manual_matmul(A, B):
+    """src/matrixOperations.cpp:7-28."""
+    A = _f(A); B = _f(B)
+    C = np.zeros((A.shape[0], B.shape[1]), order="F")
+    rc = _lib().oc_manual_matmul(_p(A), ctypes.c_long(A.shape[0]), ctypes.c_long(A.shape[1]), _p(B),
+                                 ctypes.c_long(B.shape[0]), ctypes.c_long(B.shape[1]), _p(C))
+    if rc != 0:
+        raise ValueError("Matrices dimensions are not compatible for manual matrix multiplication")
+    return C
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Comparison helpers (the reference's own notion of "matches": python/compare_rSVD.py:27-36 is a sign-agnostic
+# element-wise mean; the parity tests use the subspace-invariant quantities of SURVEY.md 8d)
+# ---------------------------------------------------------------------------------------------------------------
+def sigma_close(s, s_ref, rtol=1e-8, floor=1e-6):
+    s = np.asarray(s); s_ref = np.asarray(s_ref)
+    tol = rtol * np.maximum(s_ref, floor * s_ref[0])
+    return bool(np.all(np.abs(s - s_ref) <= tol)), float(np.max(np.abs(s - s_ref) / np.maximum(s_ref, floor * s_ref[0])))
+
+
+def subspace_sin_theta(U1, U2):
+    """sin of the largest principal angle between range(U1) and range(U2) (orthonormal columns)."""
+    M = U2 - U1 @ (U1.T @ U2)
+    return float(np.linalg.norm(M, 2))
+
+
+def reconstruction_error(A, U, S, V):
+    """||A - U diag(S) V^T||_F  (tests/rSVD_test.cpp:77-84)."""
+    return float(np.linalg.norm(A - (U * S) @ V.T))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's own first-party sources compiled over the Eigen/MPI stand-in (dev container only)
+# ---------------------------------------------------------------------------------------------------------------
+class RefLib:
+    """ctypes view of oracle/_ref/libref_rsvd.so (see oracle/ref_driver.cpp)."""
+
+    def __init__(self):
+        so = _HERE / "_ref" / "libref_rsvd.so"
+        if not so.exists():
+            build()
+        if not so.exists():
+            raise FileNotFoundError("oracle/_ref/libref_rsvd.so is not built (needs /root/reference)")
+        self.lib = ctypes.CDLL(str(so))
+
+    @staticmethod
+    def available() -> bool:
+        return (_HERE / "_ref" / "libref_rsvd.so").exists() or Path("/root/reference/src").is_dir()
+
+    def intermediate_step(self, A, Omega, l, q):
+        A = _f(A); Omega = _f(Omega); m, n = A.shape
+        Q = np.zeros((m, l), order="F")
+        self.lib.ref_intermediate_step(_p(A), ctypes.c_long(m), ctypes.c_long(n), _p(Omega), ctypes.c_int(l), ctypes.c_int(q), _p(Q))
+        return Q
+
+    def _unpack(self, U, S, V, dims):
+        d = list(dims)
+        U2 = np.array(U.ravel(order="F")[: d[0] * d[1]]).reshape((d[0], d[1]), order="F")
+        V2 = np.array(V.ravel(order="F")[: d[3] * d[4]]).reshape((d[3], d[4]), order="F")
+        return U2, S[: d[2]].copy(), V2
+
+    def rsvd(self, A, Omega, l, method=JACOBI):
+        A = _f(A); Omega = _f(Omega); m, n = A.shape; cap = max(l, n, m)
+        U = np.zeros(m * cap); S = np.zeros(cap); V = np.zeros(n * cap); dims = (ctypes.c_long * 5)()
+        rc = self.lib.ref_rsvd(_p(A), ctypes.c_long(m), ctypes.c_long(n), _p(Omega), ctypes.c_int(l), ctypes.c_int(method), _p(U), _p(S), _p(V), dims)
+        if rc != 0:
+            raise ValueError("Unsupported SVD method")
+        return self._unpack(U, S, V, dims)
+
+    def svd(self, A, method=JACOBI, r=0):
+        A = _f(A); m, n = A.shape; cap = max(m, n)
+        U = np.zeros(m * cap); S = np.zeros(cap); V = np.zeros(n * cap); dims = (ctypes.c_long * 5)()
+        rc = self.lib.ref_svd(_p(A), ctypes.c_long(m), ctypes.c_long(n), ctypes.c_int(method), ctypes.c_int(r), _p(U), _p(S), _p(V), dims)
+        if rc != 0:
+            raise ValueError("Unsupported SVD method")
+        return self._unpack(U, S, V, dims)
+
+    def qr_reduced(self, A):
+        A = _f(A); m, n = A.shape
+        Q = np.zeros((m, n), order="F"); R = np.zeros((n, n), order="F")
+        self.lib.ref_qr_reduced(_p(A), ctypes.c_long(m), ctypes.c_long(n), _p(Q), _p(R))
+        return Q, R
+
+    def qr_full(self, A):
+        A = _f(A); m, n = A.shape
+        Q = np.zeros((m, m), order="F"); R = np.zeros((m, n), order="F")
+        self.lib.ref_qr_full(_p(A), ctypes.c_long(m), ctypes.c_long(n), _p(Q), _p(R))
+        return Q, R
+
+    def manual_matmul(self, A, B):
+        A = _f(A); B = _f(B)
+        C = np.zeros((A.shape[0], B.shape[1]), order="F")
+        rc = self.lib.ref_manual_matmul(_p(A), ctypes.c_long(A.shape[0]), ctypes.c_long(A.shape[1]), _p(B), ctypes.c_long(B.shape[0]), ctypes.c_long(B.shape[1]), _p(C))
+        if rc != 0:
+            raise ValueError("Matrices dimensions are not compatible for manual matrix multiplication")
+        return C
+
+    def make_jacobi(self, x, y, z):
+        c = ctypes.c_double(); s = ctypes.c_double()
+        ok = self.lib.ref_make_jacobi(ctypes.c_double(x), ctypes.c_double(y), ctypes.c_double(z), ctypes.byref(c), ctypes.byref(s))
+        return bool(ok), c.value, s.value
+
+    def real_2x2_jacobi_svd(self, M):
+        M = _f(M); out = [ctypes.c_double() for _ in range(4)]
+        self.lib.ref_real_2x2_jacobi_svd(_p(M), *[ctypes.byref(o) for o in out])
+        return tuple(o.value for o in out)
+
+    def pm(self, A):
+        A = _f(A); m, n = A.shape
+        sigma = ctypes.c_double(); u = np.zeros(m); v = np.zeros(n)
+        self.lib.ref_pm(_p(A), ctypes.c_long(m), ctypes.c_long(n), ctypes.byref(sigma), _p(u), _p(v))
+        return sigma.value, u, v
