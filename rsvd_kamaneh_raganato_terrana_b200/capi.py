@@ -1,0 +1,64 @@
+"""ctypes binding of librsvdb.so (the C ABI declared in include/rsvdb.h).
+
+The library is the product: if it is missing or fails to load, this module raises -- there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_double, c_int, c_int64, c_void_p, POINTER
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "librsvdb.so"
+
+OK = 0
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NCCL, ERR_ALLOC, ERR_NO_CONVERGENCE, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
+SVD_JACOBI, SVD_POWER, SVD_PARALLEL_JACOBI = 0, 1, 2
+
+
+class RsvdbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rsvdb error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load librsvdb.so; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is not built. Run `python -m rsvd_kamaneh_raganato_terrana_b200.build` "
+            "(nvcc, sm_100a). There is no fallback implementation."
+        )
+    lib = ctypes.CDLL(str(LIB_PATH), mode=ctypes.RTLD_GLOBAL)
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+def _declare(lib):
+    dp = c_void_p  # device or host pointers are passed as raw addresses
+    lib.rsvdb_version.restype = c_char_p
+    lib.rsvdb_create.argtypes = [POINTER(c_void_p), c_int]
+    lib.rsvdb_destroy.argtypes = [c_void_p]
+    lib.rsvdb_set_stream.argtypes = [c_void_p, c_void_p]
+    lib.rsvdb_use_own_stream.argtypes = [c_void_p]
+    lib.rsvdb_synchronize.argtypes = [c_void_p]
+    lib.rsvdb_last_error.argtypes = [c_void_p]
+    lib.rsvdb_last_error.restype = c_char_p
+    lib.rsvdb_launch_count.argtypes = [c_void_p]
+    lib.rsvdb_launch_count.restype = c_int64
+    lib.rsvdb_gemm_an_dev.argtypes = [c_void_p, dp, c_int64, c_int64, c_int64, dp, c_int64, c_int, dp, c_int64]
+    lib.rsvdb_gemm_at_dev.argtypes = [c_void_p, dp, c_int64, c_int64, c_int64, dp, c_int64, c_int, dp, c_int64, c_int]
+
+
+def exported_symbols() -> list[str]:
+    """Symbols include/rsvdb.h declares (parsed from the header) -- used by the CPU test that the library exports them."""
+    import re
+    hdr = (_PKG.parent / "include" / "rsvdb.h").read_text()
+    return sorted(set(re.findall(r"RSVDB_API\s+[\w\s\*]+?\b(rsvdb_\w+)\s*\(", hdr)))

@@ -1,0 +1,533 @@
+// Skinny FP64 GEMMs of the rSVD range finder on sm_100a: FP64 tensor-core (DMMA) tiles fed by TMA.
+//
+//   K1  gemm_an :  Y (M x N) = A (M x K) * X (K x N)          replaces Eigen `A * Omega`, `A * Q`   (reference src/rSVD.cpp:59,66)
+//   K2  gemm_at :  Z (M x N) = A^T, A (K x M), times Q (K x N) replaces Eigen `A.transpose() * Q`    (src/rSVD.cpp:63)
+//   K3  gemm_at with transposed store: B (N x M) = Q^T A      replaces Eigen `Q.transpose() * A`     (src/rSVD.cpp:89)
+//
+// All matrices are column-major FP64 (Eigen::MatrixXd layout, include/rSVD.hpp:9).  N = l <= 128 per launch.
+//
+// Structure (both kernels): persistent CTAs, 1 TMA producer warp + 8 DMMA consumer warps, an mbarrier full/empty ring of
+// `stages` slabs of BK = 16 reduction indices.  Every smem row is 16 doubles = 128 bytes and is written by TMA with
+// SWIZZLE_128B, so that the per-lane 16-byte fragment loads below are bank-conflict free:
+//   * K1: A slab = 8 boxes {16 rows(m) x 16 k}, one per consumer warp; smem row = k, 16-byte chunk c holds rows (2c,2c+1)
+//         at chunk position c ^ (k & 7).
+//   * K2: A slab = one box {16 k(m) x 128 cols(j)}; smem row = j, chunk c holds k = (2c,2c+1) at position c ^ (j & 7).
+//   * X / Q slab = one box {16 k x 8*NB cols}; smem row = column n, chunk c holds k = (2c,2c+1) at position c ^ (n & 7).
+// The MMA is mma.sync.m16n8k4.f64 (SASS DMMA).  Index permutations (free, because the MMA does not care which matrix row
+// sits in which fragment slot) make one ld.shared.v2.f64 deliver fragment values for two MMAs:
+//   k-slot t of MMA#1 <-> k = kk+2t, of MMA#2 <-> k = kk+2t+1;  n-slot x <-> column 8j + perm(x), perm(x) = (x>>1)|((x&1)<<2);
+//   K1: m-slot g <-> row 2g, m-slot g+8 <-> row 2g+1;  K2: m-slot g <-> column perm(g), m-slot g+8 <-> column 8+perm(g).
+// Work is cut into (tile, k-split) units; with nsplit > 1 each unit stores a partial tile to a workspace and a second
+// kernel sums the partials in a fixed order (bitwise reproducible; no atomics).
+#include "gemm_dmma.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace rsvdb {
+
+namespace {
+
+constexpr int BM = 128;    // tile extent along the non-reduced dimension of A (K1: rows, K2: columns)
+constexpr int BK = 16;     // reduction slab per stage = one 128-byte swizzle row
+constexpr int NCONS = 8;   // consumer warps; each owns 16 of the BM tile rows
+constexpr int NTHREADS = (NCONS + 1) * 32;
+constexpr uint32_t A_BYTES = BM * BK * 8;
+
+struct GemmParams {
+  double* out;            // S == 1: final output; S > 1: workspace, partial s at out + s * split_stride
+  long long ld_out;
+  long long split_stride;
+  int M, N, K;            // tile dimension, l, reduction length
+  int ntiles, nsplit, kchunk;
+  int transpose_out;      // K2 only: store element (j, c) at out[c + j * ld_out]
+  int vec_ok;             // K1 only: 16-byte stores allowed
+  int stages;
+};
+
+template <int NB> struct SmemCfg {
+  static constexpr uint32_t X_BYTES = NB * 8 * BK * 8;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + X_BYTES;
+};
+
+__device__ __forceinline__ const double2* frag_ptr(const uint8_t* base, uint32_t off) {
+  return reinterpret_cast<const double2*>(base + off);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1: Y = A * X
+// ------------------------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm_an(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t STAGE = SmemCfg<NB>::STAGE_BYTES;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stages = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE);
+  uint64_t* empty = full + stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int nunits = p.ntiles * p.nsplit;
+  int stage = 0; uint32_t phase = 0;
+
+  if (warp == NCONS) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmX);
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int tile = u / p.nsplit, split = u - tile * p.nsplit;
+        const int k0 = split * p.kchunk, k1 = min(p.K, k0 + p.kchunk);
+        const int m0 = tile * BM;
+        for (int k = k0; k < k1; k += BK) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE);
+          uint8_t* sa = smem + (size_t)stage * STAGE;
+#pragma unroll
+          for (int b = 0; b < NCONS; ++b) tma_load_2d(sa + b * (16 * BK * 8), &tmA, &full[stage], m0 + 16 * b, k);
+          tma_load_2d(sa + A_BYTES, &tmX, &full[stage], k, 0);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ---------------- DMMA consumers ----------------
+    const int g = lane >> 2, t = lane & 3;
+    const int pg = (g >> 1) | ((g & 1) << 2);
+    const uint32_t offA0 = warp * (16 * BK * 8) + (2 * t) * 128 + ((g ^ (2 * t)) << 4);
+    const uint32_t offA1 = warp * (16 * BK * 8) + (2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4);
+    const uint32_t offB0 = A_BYTES + pg * 128 + ((t ^ pg) << 4);
+    const uint32_t offB1 = A_BYTES + pg * 128 + (((4 + t) ^ pg) << 4);
+
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const int tile = u / p.nsplit, split = u - tile * p.nsplit;
+      const int k0 = split * p.kchunk, k1 = min(p.K, k0 + p.kchunk);
+      double c[NB][4];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.0;
+
+      for (int k = k0; k < k1; k += BK) {
+        mbar_wait(&full[stage], phase);
+        const uint8_t* ss = smem + (size_t)stage * STAGE;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double2 a0 = *frag_ptr(ss, offA0 + h * 1024);   // rows (2g, 2g+1), k = 8h + 2t
+          const double2 a1 = *frag_ptr(ss, offA1 + h * 1024);   // rows (2g, 2g+1), k = 8h + 2t + 1
+          const uint32_t ob = h ? offB1 : offB0;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const double2 b = *frag_ptr(ss, ob + j * 1024);     // column 8j + perm(g), k = 8h + (2t, 2t+1)
+            dmma_16x8x4(c[j], a0.x, a0.y, b.x);
+            dmma_16x8x4(c[j], a1.x, a1.y, b.y);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+
+      // epilogue: thread owns rows (r, r+1), r = m0 + 16*warp + 2g, columns 8j + t and 8j + t + 4
+      double* out = p.out + (size_t)split * p.split_stride;
+      const int r = tile * BM + 16 * warp + 2 * g;
+      if (r < p.M) {
+        const bool pair = (r + 1 < p.M);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int n = 8 * j + t + 4 * e;
+            if (n < p.N) {
+              double* dst = out + (size_t)n * p.ld_out + r;
+              if (pair && p.vec_ok) {
+                *reinterpret_cast<double2*>(dst) = make_double2(c[j][e], c[j][2 + e]);
+              } else {
+                dst[0] = c[j][e];
+                if (pair) dst[1] = c[j][2 + e];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2 / K3: Z = A^T * Q   (A is K x M column-major: the reduction runs down the contiguous dimension)
+// ------------------------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm_at(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t STAGE = SmemCfg<NB>::STAGE_BYTES;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stages = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE);
+  uint64_t* empty = full + stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int nunits = p.ntiles * p.nsplit;
+  int stage = 0; uint32_t phase = 0;
+
+  if (warp == NCONS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmQ);
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int tile = u / p.nsplit, split = u - tile * p.nsplit;
+        const int k0 = split * p.kchunk, k1 = min(p.K, k0 + p.kchunk);
+        const int j0 = tile * BM;
+        for (int k = k0; k < k1; k += BK) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE);
+          uint8_t* sa = smem + (size_t)stage * STAGE;
+          tma_load_2d(sa, &tmA, &full[stage], k, j0);
+          tma_load_2d(sa + A_BYTES, &tmQ, &full[stage], k, 0);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int g = lane >> 2, t = lane & 3;
+    const int pg = (g >> 1) | ((g & 1) << 2);
+    // A slab row = tile column (16*warp + perm(g)) and (16*warp + 8 + perm(g)); both have (row & 7) == perm(g)
+    const uint32_t offAlo0 = (16 * warp + pg) * 128 + ((t ^ pg) << 4);
+    const uint32_t offAlo1 = (16 * warp + pg) * 128 + (((4 + t) ^ pg) << 4);
+    const uint32_t offB0 = A_BYTES + pg * 128 + ((t ^ pg) << 4);
+    const uint32_t offB1 = A_BYTES + pg * 128 + (((4 + t) ^ pg) << 4);
+
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const int tile = u / p.nsplit, split = u - tile * p.nsplit;
+      const int k0 = split * p.kchunk, k1 = min(p.K, k0 + p.kchunk);
+      double c[NB][4];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.0;
+
+      for (int k = k0; k < k1; k += BK) {
+        mbar_wait(&full[stage], phase);
+        const uint8_t* ss = smem + (size_t)stage * STAGE;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t oa = h ? offAlo1 : offAlo0;
+          const double2 alo = *frag_ptr(ss, oa);              // column 16w + perm(g),     k = 8h + (2t, 2t+1)
+          const double2 ahi = *frag_ptr(ss, oa + 8 * 128);    // column 16w + 8 + perm(g), k = 8h + (2t, 2t+1)
+          const uint32_t ob = h ? offB1 : offB0;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const double2 b = *frag_ptr(ss, ob + j * 1024);
+            dmma_16x8x4(c[j], alo.x, ahi.x, b.x);
+            dmma_16x8x4(c[j], alo.y, ahi.y, b.y);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+
+      // epilogue: thread owns tile columns jlo = 16w + perm(g), jhi = jlo + 8 and output columns 8j + t, 8j + t + 4
+      double* out = p.out + (size_t)split * p.split_stride;
+      const int jlo = tile * BM + 16 * warp + pg;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = 8 * j + t + 4 * e;
+          if (n < p.N) {
+            if (p.transpose_out) {
+              if (jlo < p.M) out[(size_t)jlo * p.ld_out + n] = c[j][e];
+              if (jlo + 8 < p.M) out[(size_t)(jlo + 8) * p.ld_out + n] = c[j][2 + e];
+            } else {
+              if (jlo < p.M) out[(size_t)n * p.ld_out + jlo] = c[j][e];
+              if (jlo + 8 < p.M) out[(size_t)n * p.ld_out + jlo + 8] = c[j][2 + e];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// Sum nsplit partial (rows x cols) tiles in a fixed order.  Partials are column-major with leading dimension ld_ws.
+// transpose == 0: out[r + c*ld_out]; transpose == 1: out[c + r*ld_out] (staged through shared memory so both sides coalesce).
+__global__ void k_reduce_splits(const double* __restrict__ ws, long long split_stride, int nsplit, long long ld_ws,
+                                double* __restrict__ out, long long ld_out, int rows, int cols, int transpose) {
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int r = r0 + tx, c = c0 + cc;
+    double s = 0.0;
+    if (r < rows && c < cols) {
+      const double* src = ws + (size_t)c * ld_ws + r;
+      for (int k = 0; k < nsplit; ++k) s += src[(size_t)k * split_stride];
+      if (!transpose) out[(size_t)c * ld_out + r] = s;
+    }
+    tile[cc][tx] = s;
+  }
+  if (transpose) {
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) {
+      const int r = r0 + rr, c = c0 + tx;
+      if (r < rows && c < cols) out[(size_t)r * ld_out + c] = tile[tx][rr];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Generic FP64 GEMM on CUDA cores for the small dense products off the streaming path (l x l factors, API helpers,
+// operands that TMA cannot address).  C (m x n) = alpha * op(A) * op(B) + beta * C, column-major.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int GT = 64, GKT = 16;
+__global__ void __launch_bounds__(256)
+k_gemm_generic(int ta, int tb, int m, int n, int k, double alpha, const double* __restrict__ A, long long lda,
+               const double* __restrict__ B, long long ldb, double beta, double* __restrict__ C, long long ldc) {
+  __shared__ double As[GKT][GT + 1];
+  __shared__ double Bs[GKT][GT + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < k; k0 += GKT) {
+    for (int e = threadIdx.x; e < GT * GKT; e += 256) {
+      int i, kk;
+      if (!ta) { i = e % GT; kk = e / GT; } else { kk = e % GKT; i = e / GKT; }
+      const int gi = m0 + i, gk = k0 + kk;
+      As[kk][i] = (gi < m && gk < k) ? (ta ? A[(size_t)gi * lda + gk] : A[(size_t)gk * lda + gi]) : 0.0;
+      int j, kb;
+      if (!tb) { kb = e % GKT; j = e / GKT; } else { j = e % GT; kb = e / GT; }
+      const int gj = n0 + j, gkb = k0 + kb;
+      Bs[kb][j] = (gj < n && gkb < k) ? (tb ? B[(size_t)gkb * ldb + gj] : B[(size_t)gj * ldb + gkb]) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GKT; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][tx + 16 * i]; b[i] = Bs[kk][ty + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gi = m0 + tx + 16 * i, gj = n0 + ty + 16 * j;
+      if (gi < m && gj < n) {
+        double* dst = C + (size_t)gj * ldc + gi;
+        *dst = (beta == 0.0) ? alpha * acc[i][j] : alpha * acc[i][j] + beta * (*dst);
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D FP64 column-major matrix (dim0 = rows, contiguous; dim1 = cols, stride ld), box {16 rows, box_cols}, SWIZZLE_128B.
+bool make_map(CUtensorMap* map, const double* base, long long rows, long long cols, long long ld, int box_cols) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {16, (cuuint32_t)box_cols};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool tma_addressable(const double* p, long long ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 1) == 0; }
+
+void choose_split(int ntiles, int ksteps, int nsm, int* nsplit, int* kchunk) {
+  int best = 1; double best_eff = 0.0;
+  const int smax = std::max(1, std::min(64, ksteps / 8));
+  for (int s = 1; s <= smax; ++s) {
+    const long long units = (long long)ntiles * s;
+    const double eff = (double)units / (double)(((units + nsm - 1) / nsm) * nsm);
+    if (eff > best_eff + 0.03) { best_eff = eff; best = s; }
+    if (best_eff >= 0.94) break;
+  }
+  const int per = (ksteps + best - 1) / best;
+  *kchunk = per * BK;
+  *nsplit = (ksteps + per - 1) / per;
+}
+
+template <int NB> cudaError_t launch_an(const CUtensorMap& tA, const CUtensorMap& tX, GemmParams p, int grid, cudaStream_t st) {
+  constexpr uint32_t STAGE = SmemCfg<NB>::STAGE_BYTES;
+  int stages = std::min(8, (int)((220 * 1024 - 1024) / STAGE));
+  p.stages = stages;
+  const size_t smem = (size_t)stages * STAGE + 1024 + 2 * stages * sizeof(uint64_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_an<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_gemm_an<NB><<<grid, NTHREADS, smem, st>>>(tA, tX, p);
+  return cudaGetLastError();
+}
+template <int NB> cudaError_t launch_at(const CUtensorMap& tA, const CUtensorMap& tQ, GemmParams p, int grid, cudaStream_t st) {
+  constexpr uint32_t STAGE = SmemCfg<NB>::STAGE_BYTES;
+  int stages = std::min(8, (int)((220 * 1024 - 1024) / STAGE));
+  p.stages = stages;
+  const size_t smem = (size_t)stages * STAGE + 1024 + 2 * stages * sizeof(uint64_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_at<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_gemm_at<NB><<<grid, NTHREADS, smem, st>>>(tA, tQ, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t gemm_generic(cudaStream_t st, int ta, int tb, int m, int n, int k, double alpha, const double* A, long long lda,
+                         const double* B, long long ldb, double beta, double* C, long long ldc) {
+  if (m <= 0 || n <= 0) return cudaSuccess;
+  dim3 grid((m + GT - 1) / GT, (n + GT - 1) / GT);
+  k_gemm_generic<<<grid, 256, 0, st>>>(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  return cudaGetLastError();
+}
+
+cudaError_t gemm_an(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A, long long M, long long K, long long lda,
+                    const double* X, long long ldx, int N, double* Y, long long ldy, int* launches) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (K <= 0) {
+    for (int n = 0; n < N; ++n) { cudaError_t e = cudaMemsetAsync(Y + (size_t)n * ldy, 0, (size_t)M * 8, st); if (e != cudaSuccess) return e; }
+    return cudaSuccess;
+  }
+  if (!tma_addressable(A, lda) || !tma_addressable(X, ldx) || M >= (1LL << 31) || K >= (1LL << 31)) {
+    if (launches) ++*launches;
+    return gemm_generic(st, 0, 0, (int)M, N, (int)K, 1.0, A, lda, X, ldx, 0.0, Y, ldy);
+  }
+  CUtensorMap tA;
+  if (!make_map(&tA, A, M, K, lda, BK)) return cudaErrorInvalidValue;
+  const int ntiles = (int)((M + BM - 1) / BM), ksteps = (int)((K + BK - 1) / BK);
+  int nsplit, kchunk; choose_split(ntiles, ksteps, nsm, &nsplit, &kchunk);
+  for (int n0 = 0; n0 < N; n0 += 128) {
+    const int nc = std::min(128, N - n0), NB = (nc + 7) / 8;
+    CUtensorMap tX;
+    if (!make_map(&tX, X + (size_t)n0 * ldx, K, nc, ldx, NB * 8)) return cudaErrorInvalidValue;
+    GemmParams p{};
+    p.M = (int)M; p.N = nc; p.K = (int)K; p.ntiles = ntiles; p.nsplit = nsplit; p.kchunk = kchunk; p.transpose_out = 0;
+    double* yout = Y + (size_t)n0 * ldy;
+    if (nsplit == 1) {
+      p.out = yout; p.ld_out = ldy; p.split_stride = 0;
+      p.vec_ok = ((ldy & 1) == 0 && (reinterpret_cast<uintptr_t>(yout) & 15) == 0) ? 1 : 0;
+    } else {
+      const long long ldw = (M + 1) & ~1LL;
+      const size_t need = (size_t)nsplit * ldw * nc * 8;
+      cudaError_t e = ws.reserve(need); if (e != cudaSuccess) return e;
+      p.out = ws.ptr; p.ld_out = ldw; p.split_stride = ldw * nc; p.vec_ok = 1;
+    }
+    const int grid = std::min(nsm, ntiles * nsplit);
+    cudaError_t e;
+    switch (NB) {
+      case 1: e = launch_an<1>(tA, tX, p, grid, st); break;   case 2: e = launch_an<2>(tA, tX, p, grid, st); break;
+      case 3: e = launch_an<3>(tA, tX, p, grid, st); break;   case 4: e = launch_an<4>(tA, tX, p, grid, st); break;
+      case 5: e = launch_an<5>(tA, tX, p, grid, st); break;   case 6: e = launch_an<6>(tA, tX, p, grid, st); break;
+      case 7: e = launch_an<7>(tA, tX, p, grid, st); break;   case 8: e = launch_an<8>(tA, tX, p, grid, st); break;
+      case 9: e = launch_an<9>(tA, tX, p, grid, st); break;   case 10: e = launch_an<10>(tA, tX, p, grid, st); break;
+      case 11: e = launch_an<11>(tA, tX, p, grid, st); break; case 12: e = launch_an<12>(tA, tX, p, grid, st); break;
+      case 13: e = launch_an<13>(tA, tX, p, grid, st); break; case 14: e = launch_an<14>(tA, tX, p, grid, st); break;
+      case 15: e = launch_an<15>(tA, tX, p, grid, st); break; default: e = launch_an<16>(tA, tX, p, grid, st); break;
+    }
+    if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+    if (nsplit > 1) {
+      dim3 rg((unsigned)((M + 31) / 32), (unsigned)((nc + 31) / 32));
+      k_reduce_splits<<<rg, dim3(32, 8), 0, st>>>(ws.ptr, p.split_stride, nsplit, p.ld_out, yout, ldy, (int)M, nc, 0);
+      e = cudaGetLastError(); if (e != cudaSuccess) return e;
+      if (launches) ++*launches;
+    }
+  }
+  return cudaSuccess;
+}
+
+cudaError_t gemm_at(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A, long long K, long long M, long long lda,
+                    const double* Q, long long ldq, int N, double* Z, long long ldz, int transpose_out, int* launches) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (K <= 0) {
+    if (!transpose_out) { for (int n = 0; n < N; ++n) { cudaError_t e = cudaMemsetAsync(Z + (size_t)n * ldz, 0, (size_t)M * 8, st); if (e != cudaSuccess) return e; } }
+    else { for (long long j = 0; j < M; ++j) { cudaError_t e = cudaMemsetAsync(Z + (size_t)j * ldz, 0, (size_t)N * 8, st); if (e != cudaSuccess) return e; } }
+    return cudaSuccess;
+  }
+  if (!tma_addressable(A, lda) || !tma_addressable(Q, ldq) || M >= (1LL << 31) || K >= (1LL << 31)) {
+    if (launches) ++*launches;
+    if (!transpose_out) return gemm_generic(st, 1, 0, (int)M, N, (int)K, 1.0, A, lda, Q, ldq, 0.0, Z, ldz);
+    return gemm_generic(st, 1, 0, N, (int)M, (int)K, 1.0, Q, ldq, A, lda, 0.0, Z, ldz);
+  }
+  CUtensorMap tA;
+  if (!make_map(&tA, A, K, M, lda, BM)) return cudaErrorInvalidValue;
+  const int ntiles = (int)((M + BM - 1) / BM), ksteps = (int)((K + BK - 1) / BK);
+  int nsplit, kchunk; choose_split(ntiles, ksteps, nsm, &nsplit, &kchunk);
+  for (int n0 = 0; n0 < N; n0 += 128) {
+    const int nc = std::min(128, N - n0), NB = (nc + 7) / 8;
+    CUtensorMap tQ;
+    if (!make_map(&tQ, Q + (size_t)n0 * ldq, K, nc, ldq, NB * 8)) return cudaErrorInvalidValue;
+    GemmParams p{};
+    p.M = (int)M; p.N = nc; p.K = (int)K; p.ntiles = ntiles; p.nsplit = nsplit; p.kchunk = kchunk; p.vec_ok = 0;
+    double* zout = transpose_out ? Z + n0 : Z + (size_t)n0 * ldz;
+    if (nsplit == 1) {
+      p.out = zout; p.ld_out = ldz; p.split_stride = 0; p.transpose_out = transpose_out;
+    } else {
+      const size_t need = (size_t)nsplit * M * nc * 8;
+      cudaError_t e = ws.reserve(need); if (e != cudaSuccess) return e;
+      p.out = ws.ptr; p.ld_out = M; p.split_stride = M * nc; p.transpose_out = 0;
+    }
+    const int grid = std::min(nsm, ntiles * nsplit);
+    cudaError_t e;
+    switch (NB) {
+      case 1: e = launch_at<1>(tA, tQ, p, grid, st); break;   case 2: e = launch_at<2>(tA, tQ, p, grid, st); break;
+      case 3: e = launch_at<3>(tA, tQ, p, grid, st); break;   case 4: e = launch_at<4>(tA, tQ, p, grid, st); break;
+      case 5: e = launch_at<5>(tA, tQ, p, grid, st); break;   case 6: e = launch_at<6>(tA, tQ, p, grid, st); break;
+      case 7: e = launch_at<7>(tA, tQ, p, grid, st); break;   case 8: e = launch_at<8>(tA, tQ, p, grid, st); break;
+      case 9: e = launch_at<9>(tA, tQ, p, grid, st); break;   case 10: e = launch_at<10>(tA, tQ, p, grid, st); break;
+      case 11: e = launch_at<11>(tA, tQ, p, grid, st); break; case 12: e = launch_at<12>(tA, tQ, p, grid, st); break;
+      case 13: e = launch_at<13>(tA, tQ, p, grid, st); break; case 14: e = launch_at<14>(tA, tQ, p, grid, st); break;
+      case 15: e = launch_at<15>(tA, tQ, p, grid, st); break; default: e = launch_at<16>(tA, tQ, p, grid, st); break;
+    }
+    if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+    if (nsplit > 1) {
+      dim3 rg((unsigned)((M + 31) / 32), (unsigned)((nc + 31) / 32));
+      k_reduce_splits<<<rg, dim3(32, 8), 0, st>>>(ws.ptr, p.split_stride, nsplit, p.ld_out, zout, ldz, (int)M, nc, transpose_out);
+      e = cudaGetLastError(); if (e != cudaSuccess) return e;
+      if (launches) ++*launches;
+    }
+  }
+  return cudaSuccess;
+}
+
+}  // namespace rsvdb
