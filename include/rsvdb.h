@@ -58,14 +58,81 @@ RSVDB_API const char* rsvdb_version(void);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 RSVDB_API int64_t rsvdb_launch_count(const rsvdb_ctx* ctx);
 
+/* Optional per-phase device timing (CUDA events on the context's stream).  rsvdb_phase_ms synchronises the stream,
+ * writes the accumulated milliseconds per phase since the last call and clears them.
+ * Phases: 0 A*X GEMMs, 1 A^T*Q GEMMs, 2 TSQR, 3 small SVD (includes its own QR), 4 collectives, 5 other, 6 host<->device copies. */
+#define RSVDB_NUM_PHASES 7
+RSVDB_API int rsvdb_set_profiling(rsvdb_ctx* ctx, int enabled);
+RSVDB_API int rsvdb_phase_ms(rsvdb_ctx* ctx, double* out_ms /* RSVDB_NUM_PHASES */);
+/* Sweeps (negative: hit the cap without converging) and plane rotations of the last Jacobi small SVD. Synchronises. */
+RSVDB_API int rsvdb_last_svd_info(rsvdb_ctx* ctx, int* sweeps, int* rotations);
+
+/* ---- multi-GPU: one process per GPU, A row-sharded ------------------------------------------------------
+ * The reference's only process boundary on this path is MPI_Gatherv/MPI_Bcast of Omega (src/rSVD.cpp:49,52) -- every MPI
+ * rank repeats the whole computation.  Here rank p holds rows [offset_p, offset_p + m_p) of A; the engine all-reduces the
+ * n x l partial sums of A^T Q and all-gathers the l x l TSQR R factors over NCCL (NVLink); everything else is shard-local.
+ * The 128-byte NCCL unique id is produced on rank 0 and handed to every rank by the launcher (torch.distributed, MPI, ...). */
+RSVDB_API int rsvdb_comm_unique_id(void* out_id_128_bytes);
+RSVDB_API int rsvdb_comm_init(rsvdb_ctx* ctx, int nranks, int rank, const void* id_128_bytes);
+RSVDB_API int rsvdb_comm_size(const rsvdb_ctx* ctx);
+RSVDB_API int rsvdb_comm_rank(const rsvdb_ctx* ctx);
+
 /* ---- dense building blocks, device pointers -------------------------------------------------------------------- */
 /* Y (m x l) = A (m x n) * X (n x l).            Replaces Eigen `A * Omega`, `A * Q` at src/rSVD.cpp:59,66. */
 RSVDB_API int rsvdb_gemm_an_dev(rsvdb_ctx* ctx, const double* dA, int64_t m, int64_t n, int64_t lda, const double* dX, int64_t ldx,
-                      int l, double* dY, int64_t ldy);
+                                int l, double* dY, int64_t ldy);
 /* Z (n x l) = A^T * Q, A m x n, Q m x l.        Replaces Eigen `A.transpose() * Q` at src/rSVD.cpp:63.
- * transpose_out != 0 stores B (l x n) = Q^T * A instead -- Eigen `Q.transpose() * A` at src/rSVD.cpp:89. */
+ * transpose_out != 0 stores B (l x n) = Q^T * A instead -- Eigen `Q.transpose() * A` at src/rSVD.cpp:89.
+ * Shard-local: no reduction over ranks is performed here. */
 RSVDB_API int rsvdb_gemm_at_dev(rsvdb_ctx* ctx, const double* dA, int64_t m, int64_t n, int64_t lda, const double* dQ, int64_t ldq,
-                      int l, double* dZ, int64_t ldz, int transpose_out);
+                                int l, double* dZ, int64_t ldz, int transpose_out);
+/* In-place thin Householder QR (TSQR): Y (rows x l) <- Q.  Replaces `HouseholderQR qr(Y); Q = qr.householderQ() *
+ * Identity(rows, l)` at src/rSVD.cpp:60-61,64-65,67-68.  dR (optional, l x l, leading dimension l) receives R.
+ * sharded != 0: Y is this rank's row block and the R factors are combined across ranks. */
+RSVDB_API int rsvdb_qr_dev(rsvdb_ctx* ctx, double* dY, int64_t rows, int l, int64_t ldy, int sharded, double* dR);
+/* intermediate_step(A, Q, Omega, l, q) -- include/rSVD.hpp:13, src/rSVD.cpp:57-70.  A: this rank's m_local x n row block. */
+RSVDB_API int rsvdb_range_finder_dev(rsvdb_ctx* ctx, const double* dA, int64_t m_local, int64_t n, int64_t lda,
+                                     const double* dOmega, int64_t ldo, int l, int q, double* dQ, int64_t ldq);
+/* rSVD(A, U, S, V, l, method) -- include/rSVD.hpp:14, src/rSVD.cpp:72-133 -- with Omega and q (hard-coded 2 in the
+ * reference, :83) as arguments.  U: m_local x k, S: k, V: n x k, k = min(l, n).  For RSVDB_SVD_POWER, U gets the
+ * reference's identity-completed l columns and V holds the right singular vectors in COLUMNS (n x k); the drop-in
+ * wrappers re-shape V to the reference's n x n rows layout (include/SVD_class.hpp:214). */
+RSVDB_API int rsvdb_rsvd_dev(rsvdb_ctx* ctx, const double* dA, int64_t m_local, int64_t n, int64_t lda, const double* dOmega,
+                             int64_t ldo, int l, int q, int method, uint64_t seed, double* dU, int64_t ldu, double* dS,
+                             double* dV, int64_t ldv);
+/* N(0,1) n x l test matrix on the device (counter-based generator; replaces generateOmega, src/rSVD.cpp:12-55, whose
+ * std::random_device draw is not reproducible).  Every rank that passes the same seed gets the same Omega. */
+RSVDB_API int rsvdb_generate_omega_dev(rsvdb_ctx* ctx, int64_t n, int l, uint64_t seed, double* dOmega, int64_t ldo);
+
+/* ---- reference API mirrors, host pointers (H2D / D2H inside) ------------------------------------------------------ */
+/* rSVD (src/rSVD.cpp:72-133).  Omega == NULL: drawn on the device from `seed`.  A is this rank's row block. */
+RSVDB_API int rsvdb_rsvd_host(rsvdb_ctx* ctx, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
+                              uint64_t seed, int l, int q, int method, double* U, int64_t ldu, double* S, double* V, int64_t ldv);
+/* intermediate_step (src/rSVD.cpp:57-70). */
+RSVDB_API int rsvdb_intermediate_step_host(rsvdb_ctx* ctx, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega,
+                                           int64_t ldo, int l, int q, double* Q, int64_t ldq);
+/* generateOmega (src/rSVD.cpp:12-55). */
+RSVDB_API int rsvdb_generate_omega_host(rsvdb_ctx* ctx, int64_t n, int l, uint64_t seed, double* Omega, int64_t ldo);
+/* SVD<method>(A, r).compute() -- include/SVD_class.hpp:35-97.  k = min(m, n).
+ *   Jacobi / ParallelJacobi: U m x k, S k, V n x k (columns), *found = k.
+ *   Power: U m x m (identity-completed), S k, V n x dim (columns; dim = r ? r : k), *found = number of triplets before
+ *   the reference's sigma < 1e-12 early exit (:198-209). */
+RSVDB_API int rsvdb_svd_host(rsvdb_ctx* ctx, const double* A, int64_t m, int64_t n, int64_t lda, int method, int r, uint64_t seed,
+                             double* U, int64_t ldu, double* S, double* V, int64_t ldv, int* found);
+/* qr_decomposition_reduced / qr_decomposition_full (include/QR.hpp:15-16, src/QR.cpp:22-80) and the QR class
+ * (image_compression/include/QR.hpp:13-64).  reduced (full == 0, m >= n): Q m x n, R n x n.  full: Q m x m, R m x n.
+ * Householder-based; rows of R / columns of Q are sign-normalised so that diag(R) >= 0 (the Givens convention). */
+RSVDB_API int rsvdb_qr_host(rsvdb_ctx* ctx, const double* A, int64_t m, int64_t n, int64_t lda, int full, double* Q, int64_t ldq,
+                            double* R, int64_t ldr);
+/* PM(A, B, sigma, u, v) -- include/PM.hpp:18, src/PM.cpp:4-81.  B = A^T A is not needed (see power.cu). */
+RSVDB_API int rsvdb_pm_host(rsvdb_ctx* ctx, const double* A, int64_t m, int64_t n, int64_t lda, uint64_t seed, double* sigma,
+                            double* u, double* v);
+/* manualMatrixMultiply(A, B) -- include/matrixOperations.hpp:14, src/matrixOperations.cpp:7-28.
+ * Returns RSVDB_ERR_INVALID_ARGUMENT when ka != kb (the reference throws std::invalid_argument, :8-11). */
+RSVDB_API int rsvdb_gemm_host(rsvdb_ctx* ctx, const double* A, int64_t m, int64_t ka, int64_t lda, const double* B, int64_t kb,
+                              int64_t n, int64_t ldb, double* C, int64_t ldc);
+/* Number of power iterations PM runs for an n-column matrix (src/PM.cpp:25-28). */
+RSVDB_API int rsvdb_pm_iterations(int64_t ncols);
 
 #ifdef __cplusplus
 }

@@ -42,19 +42,43 @@ def load() -> ctypes.CDLL:
 
 
 def _declare(lib):
-    dp = c_void_p  # device or host pointers are passed as raw addresses
+    vp = c_void_p  # device or host pointers are passed as raw addresses
+    i64, u64 = c_int64, ctypes.c_uint64
     lib.rsvdb_version.restype = c_char_p
-    lib.rsvdb_create.argtypes = [POINTER(c_void_p), c_int]
-    lib.rsvdb_destroy.argtypes = [c_void_p]
-    lib.rsvdb_set_stream.argtypes = [c_void_p, c_void_p]
-    lib.rsvdb_use_own_stream.argtypes = [c_void_p]
-    lib.rsvdb_synchronize.argtypes = [c_void_p]
-    lib.rsvdb_last_error.argtypes = [c_void_p]
     lib.rsvdb_last_error.restype = c_char_p
-    lib.rsvdb_launch_count.argtypes = [c_void_p]
     lib.rsvdb_launch_count.restype = c_int64
-    lib.rsvdb_gemm_an_dev.argtypes = [c_void_p, dp, c_int64, c_int64, c_int64, dp, c_int64, c_int, dp, c_int64]
-    lib.rsvdb_gemm_at_dev.argtypes = [c_void_p, dp, c_int64, c_int64, c_int64, dp, c_int64, c_int, dp, c_int64, c_int]
+    sig = {
+        "rsvdb_create": [POINTER(c_void_p), c_int],
+        "rsvdb_destroy": [vp],
+        "rsvdb_set_stream": [vp, vp],
+        "rsvdb_use_own_stream": [vp],
+        "rsvdb_synchronize": [vp],
+        "rsvdb_last_error": [vp],
+        "rsvdb_launch_count": [vp],
+        "rsvdb_set_profiling": [vp, c_int],
+        "rsvdb_phase_ms": [vp, POINTER(c_double)],
+        "rsvdb_last_svd_info": [vp, POINTER(c_int), POINTER(c_int)],
+        "rsvdb_comm_unique_id": [vp],
+        "rsvdb_comm_init": [vp, c_int, c_int, vp],
+        "rsvdb_comm_size": [vp],
+        "rsvdb_comm_rank": [vp],
+        "rsvdb_pm_iterations": [i64],
+        "rsvdb_gemm_an_dev": [vp, vp, i64, i64, i64, vp, i64, c_int, vp, i64],
+        "rsvdb_gemm_at_dev": [vp, vp, i64, i64, i64, vp, i64, c_int, vp, i64, c_int],
+        "rsvdb_qr_dev": [vp, vp, i64, c_int, i64, c_int, vp],
+        "rsvdb_range_finder_dev": [vp, vp, i64, i64, i64, vp, i64, c_int, c_int, vp, i64],
+        "rsvdb_rsvd_dev": [vp, vp, i64, i64, i64, vp, i64, c_int, c_int, c_int, u64, vp, i64, vp, vp, i64],
+        "rsvdb_generate_omega_dev": [vp, i64, c_int, u64, vp, i64],
+        "rsvdb_rsvd_host": [vp, vp, i64, i64, i64, vp, i64, u64, c_int, c_int, c_int, vp, i64, vp, vp, i64],
+        "rsvdb_intermediate_step_host": [vp, vp, i64, i64, i64, vp, i64, c_int, c_int, vp, i64],
+        "rsvdb_generate_omega_host": [vp, i64, c_int, u64, vp, i64],
+        "rsvdb_svd_host": [vp, vp, i64, i64, i64, c_int, c_int, u64, vp, i64, vp, vp, i64, POINTER(c_int)],
+        "rsvdb_qr_host": [vp, vp, i64, i64, i64, c_int, vp, i64, vp, i64],
+        "rsvdb_pm_host": [vp, vp, i64, i64, i64, u64, POINTER(c_double), vp, vp],
+        "rsvdb_gemm_host": [vp, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64],
+    }
+    for name, argtypes in sig.items():
+        getattr(lib, name).argtypes = argtypes
 
 
 def exported_symbols() -> list[str]:

@@ -1,8 +1,68 @@
-// C ABI (include/rsvdb.h): context management and the dense building blocks.
+// C ABI (include/rsvdb.h): context management, device entry points and the host-pointer mirrors of the reference API.
 #include "../../include/rsvdb.h"
+
+#include <algorithm>
+#include <vector>
+
+#include "comm.cuh"
 #include "context.cuh"
+#include "pipeline.cuh"
+#include "tsqr.cuh"
 
 using namespace rsvdb;
+
+namespace {
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// K9: Omega(i, j) ~ N(0,1), a pure function of (seed, i, j): identical on every rank and for every launch geometry.
+__global__ void k_fill_normal(double* __restrict__ out, long long ld, long long rows, int cols, uint64_t seed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  for (int j = blockIdx.y; j < cols; j += gridDim.y) {
+    const uint64_t idx = (uint64_t)j * (uint64_t)rows + (uint64_t)i;
+    const uint64_t a = mix64(seed ^ mix64(2 * idx)), b = mix64(seed ^ mix64(2 * idx + 1));
+    const double u1 = ((a >> 11) + 1.0) * (1.0 / 9007199254740993.0), u2 = (b >> 11) * (1.0 / 9007199254740992.0);
+    out[(size_t)j * ld + i] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+  }
+}
+// Givens sign convention for the QR API: make diag(R) >= 0 by flipping row i of R and column i of Q together.
+__global__ void k_sign_normalise(double* __restrict__ Q, long long ldq, long long qrows, double* __restrict__ R, long long ldr,
+                                 int rcols, int k) {
+  const int i = blockIdx.x;   // reflector / diagonal index
+  if (i >= k) return;
+  const double d = R[(size_t)i * ldr + i];
+  if (!(d < 0.0)) return;
+  for (int j = threadIdx.x; j < rcols; j += blockDim.x) R[(size_t)j * ldr + i] = -R[(size_t)j * ldr + i];
+  for (long long r = threadIdx.x; r < qrows; r += blockDim.x) Q[(size_t)i * ldq + r] = -Q[(size_t)i * ldq + r];
+}
+
+inline int64_t even_ld(int64_t rows) { return std::max<int64_t>(2, (rows + 1) & ~int64_t(1)); }
+
+int h2d(rsvdb_ctx* c, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  PhaseTimer pt(c, PH_COPY);
+  RSVDB_CUDA(c, cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+int d2h(rsvdb_ctx* c, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  PhaseTimer pt(c, PH_COPY);
+  RSVDB_CUDA(c, cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+// bump allocator over io_ws
+struct IoArena {
+  rsvdb_ctx* c; size_t off = 0;
+  explicit IoArena(rsvdb_ctx* ctx) : c(ctx) {}
+  static size_t pad(size_t doubles) { return (doubles + 31) & ~size_t(31); }
+  double* take(size_t doubles) { double* p = c->io_ws.ptr + off; off += pad(doubles); return p; }
+};
+
+}  // namespace
 
 extern "C" {
 
@@ -30,7 +90,10 @@ int rsvdb_destroy(rsvdb_ctx* c) {
   if (!c) return RSVDB_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->gemm_ws.release(); c->qr_ws.release(); c->tmp_ws.release(); c->io_ws.release();
+  comm_destroy(c);
+  for (auto& s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  for (auto e : c->event_pool) cudaEventDestroy(e);
+  c->gemm_ws.release(); c->qr_ws.release(); c->qr2_ws.release(); c->tmp_ws.release(); c->svd_ws.release(); c->io_ws.release();
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return RSVDB_OK;
@@ -41,22 +104,66 @@ int rsvdb_set_stream(rsvdb_ctx* c, void* s) {
   c->stream = static_cast<cudaStream_t>(s);
   return RSVDB_OK;
 }
-
 int rsvdb_use_own_stream(rsvdb_ctx* c) {
   if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
   c->stream = c->own_stream;
   return RSVDB_OK;
 }
-
 int rsvdb_synchronize(rsvdb_ctx* c) {
   if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
   RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RSVDB_OK;
 }
-
 const char* rsvdb_last_error(const rsvdb_ctx* c) { return c ? c->err.c_str() : "null context"; }
 int64_t rsvdb_launch_count(const rsvdb_ctx* c) { return c ? c->launches : 0; }
 
+int rsvdb_set_profiling(rsvdb_ctx* c, int enabled) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  c->profiling = enabled != 0;
+  return RSVDB_OK;
+}
+int rsvdb_phase_ms(rsvdb_ctx* c, double* out) {
+  if (!c || !out) return RSVDB_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < RSVDB_NUM_PHASES; ++i) out[i] = 0.0;
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (auto& s : c->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess && s.phase >= 0 && s.phase < RSVDB_NUM_PHASES) out[s.phase] += ms;
+    c->event_pool.push_back(s.a); c->event_pool.push_back(s.b);
+  }
+  c->spans.clear();
+  return RSVDB_OK;
+}
+int rsvdb_last_svd_info(rsvdb_ctx* c, int* sweeps, int* rotations) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  int h[2] = {0, 0};
+  if (c->d_svd_info) {
+    RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+    RSVDB_CUDA(c, cudaMemcpy(h, c->d_svd_info, sizeof(h), cudaMemcpyDeviceToHost));
+  }
+  if (sweeps) *sweeps = h[0];
+  if (rotations) *rotations = h[1];
+  return RSVDB_OK;
+}
+
+int rsvdb_comm_unique_id(void* out) {
+  if (!out) return RSVDB_ERR_INVALID_ARGUMENT;
+  std::string err;
+  return comm_unique_id(out, &err);
+}
+int rsvdb_comm_init(rsvdb_ctx* c, int nranks, int rank, const void* id) {
+  if (!c || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "comm_init: bad rank/size");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  return comm_init(c, nranks, rank, id);
+}
+int rsvdb_comm_size(const rsvdb_ctx* c) { return c ? c->nranks : 0; }
+int rsvdb_comm_rank(const rsvdb_ctx* c) { return c ? c->rank : 0; }
+
+int rsvdb_pm_iterations(int64_t ncols) { return pm_iterations(ncols); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// device entry points
+// ---------------------------------------------------------------------------------------------------------------------
 int rsvdb_gemm_an_dev(rsvdb_ctx* c, const double* dA, int64_t m, int64_t n, int64_t lda, const double* dX, int64_t ldx,
                       int l, double* dY, int64_t ldy) {
   if (!c || m < 0 || n < 0 || l < 0 || lda < m || ldx < n || ldy < m) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "gemm_an: bad shape");
@@ -73,6 +180,226 @@ int rsvdb_gemm_at_dev(rsvdb_ctx* c, const double* dA, int64_t m, int64_t n, int6
   int k = 0;
   RSVDB_CUDA(c, gemm_at(c->gemm_ws, c->stream, c->nsm, dA, m, n, lda, dQ, ldq, l, dZ, ldz, transpose_out, &k));
   c->launches += k;
+  return RSVDB_OK;
+}
+
+int rsvdb_qr_dev(rsvdb_ctx* c, double* dY, int64_t rows, int l, int64_t ldy, int sharded, double* dR) {
+  if (!c || rows < 0 || l <= 0 || ldy < rows) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "qr: bad shape");
+  const double* R = nullptr;
+  RSVDB_TRY(qr_inplace(c, dY, rows, l, ldy, sharded != 0, &R));
+  if (dR) RSVDB_CUDA(c, cudaMemcpyAsync(dR, R, (size_t)l * l * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_range_finder_dev(rsvdb_ctx* c, const double* dA, int64_t m, int64_t n, int64_t lda, const double* dOmega, int64_t ldo,
+                           int l, int q, double* dQ, int64_t ldq) {
+  if (!c || m < 0 || n <= 0 || lda < m || ldo < n || ldq < m) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "range_finder: bad shape");
+  return range_finder(c, dA, m, n, lda, dOmega, ldo, l, q, dQ, ldq);
+}
+
+int rsvdb_rsvd_dev(rsvdb_ctx* c, const double* dA, int64_t m, int64_t n, int64_t lda, const double* dOmega, int64_t ldo, int l,
+                   int q, int method, uint64_t seed, double* dU, int64_t ldu, double* dS, double* dV, int64_t ldv) {
+  if (!c || m < 0 || n <= 0 || lda < m || ldo < n || ldu < m || ldv < n) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "rsvd: bad shape");
+  return rsvd_device(c, dA, m, n, lda, dOmega, ldo, l, q, method, dU, ldu, dS, dV, ldv, seed);
+}
+
+int rsvdb_generate_omega_dev(rsvdb_ctx* c, int64_t n, int l, uint64_t seed, double* dOmega, int64_t ldo) {
+  if (!c || n < 0 || l < 0 || ldo < n) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "generate_omega: bad shape");
+  if (n == 0 || l == 0) return RSVDB_OK;
+  dim3 g((unsigned)((n + 255) / 256), (unsigned)std::min(l, 128));
+  k_fill_normal<<<g, 256, 0, c->stream>>>(dOmega, ldo, n, l, seed);
+  RSVDB_CUDA(c, cudaGetLastError());
+  ++c->launches;
+  return RSVDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host-pointer mirrors of the reference API
+// ---------------------------------------------------------------------------------------------------------------------
+int rsvdb_generate_omega_host(rsvdb_ctx* c, int64_t n, int l, uint64_t seed, double* Omega, int64_t ldo) {
+  if (!c || !Omega || n < 0 || l < 0 || ldo < n) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "generate_omega: bad shape");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  RSVDB_CUDA(c, c->io_ws.reserve(IoArena::pad((size_t)n * l) * 8 + 256));
+  IoArena ar(c); double* dO = ar.take((size_t)n * l);
+  RSVDB_TRY(rsvdb_generate_omega_dev(c, n, l, seed, dO, n));
+  RSVDB_TRY(d2h(c, Omega, ldo, dO, n, n, l));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_intermediate_step_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
+                                 int l, int q, double* Q, int64_t ldq) {
+  if (!c || !A || !Omega || !Q || m < 0 || n <= 0 || l <= 0 || q < 0 || lda < m || ldo < n || ldq < m)
+    return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "intermediate_step: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t ldA = even_ld(m), ldO = even_ld(n);
+  const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)ldO * l) + IoArena::pad((size_t)ldA * l)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  double* dA = ar.take((size_t)ldA * n); double* dO = ar.take((size_t)ldO * l); double* dQ = ar.take((size_t)ldA * l);
+  RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
+  RSVDB_TRY(h2d(c, dO, ldO, Omega, ldo, n, l));
+  RSVDB_TRY(range_finder(c, dA, m, n, ldA, dO, ldO, l, q, dQ, ldA));
+  RSVDB_TRY(d2h(c, Q, ldq, dQ, ldA, m, l));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_rsvd_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega, int64_t ldo, uint64_t seed,
+                    int l, int q, int method, double* U, int64_t ldu, double* S, double* V, int64_t ldv) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (method != 0 && method != 1 && method != 2) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "Unsupported SVD method");
+  if (!A || !U || !S || !V || m < 0 || n <= 0 || l <= 0 || q < 0 || lda < m || (Omega && ldo < n) || ldu < m || ldv < n)
+    return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "rSVD: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t k = std::min<int64_t>(l, n);
+  const int64_t ldA = even_ld(m), ldO = even_ld(n);
+  const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)ldO * l) + IoArena::pad((size_t)ldA * l) +
+                       IoArena::pad((size_t)ldO * l) + IoArena::pad((size_t)l)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  double* dA = ar.take((size_t)ldA * n); double* dO = ar.take((size_t)ldO * l); double* dU = ar.take((size_t)ldA * l);
+  double* dV = ar.take((size_t)ldO * l); double* dS = ar.take((size_t)l);
+  RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
+  if (Omega) { RSVDB_TRY(h2d(c, dO, ldO, Omega, ldo, n, l)); }
+  else { RSVDB_TRY(rsvdb_generate_omega_dev(c, n, l, seed, dO, ldO)); }
+  RSVDB_TRY(rsvd_device(c, dA, m, n, ldA, dO, ldO, l, q, method, dU, ldA, dS, dV, ldO, seed));
+  RSVDB_TRY(d2h(c, U, ldu, dU, ldA, m, k));
+  RSVDB_TRY(d2h(c, S, k, dS, k, k, 1));
+  RSVDB_TRY(d2h(c, V, ldv, dV, ldO, n, k));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_svd_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, int method, int r, uint64_t seed, double* U,
+                   int64_t ldu, double* S, double* V, int64_t ldv, int* found) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (method != 0 && method != 1 && method != 2) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "Unsupported SVD method");
+  if (!A || !U || !S || !V || m <= 0 || n <= 0 || lda < m || ldu < m || ldv < n || r < 0)
+    return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "SVD: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t k = std::min(m, n);
+  const int64_t ldA = even_ld(m), ldN = even_ld(n);
+  if (method == RSVDB_SVD_POWER) {
+    const int dim = r ? r : (int)k;
+    if (dim > k) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "SVD<Power>: r larger than min(rows, cols)");
+    const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)ldN * m) + IoArena::pad((size_t)ldA * m) +
+                         IoArena::pad((size_t)ldN * dim) + IoArena::pad((size_t)k)) * 8 + 256;
+    RSVDB_CUDA(c, c->io_ws.reserve(need));
+    IoArena ar(c);
+    double* dA = ar.take((size_t)ldA * n); double* dAt = ar.take((size_t)ldN * m); double* dU = ar.take((size_t)ldA * m);
+    double* dV = ar.take((size_t)ldN * dim); double* dS = ar.take((size_t)k);
+    RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
+    RSVDB_TRY(transpose2d(c, dA, ldA, dAt, ldN, m, n));
+    int f = 0;
+    RSVDB_TRY(small_svd_power_t(c, dAt, ldN, m, n, r, seed, dU, ldA, (int)m, dS, dV, ldN, &f));
+    RSVDB_TRY(d2h(c, U, ldu, dU, ldA, m, m));
+    RSVDB_TRY(d2h(c, S, k, dS, k, k, 1));
+    RSVDB_TRY(d2h(c, V, ldv, dV, ldN, n, dim));
+    RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (found) *found = f;
+    return RSVDB_OK;
+  }
+  const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)ldA * k) + IoArena::pad((size_t)ldN * k) +
+                       IoArena::pad((size_t)k)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  double* dA = ar.take((size_t)ldA * n); double* dU = ar.take((size_t)ldA * k); double* dV = ar.take((size_t)ldN * k);
+  double* dS = ar.take((size_t)k);
+  RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
+  RSVDB_TRY(small_svd_jacobi(c, dA, ldA, nullptr, 0, m, n, dU, ldA, dS, dV, ldN));
+  RSVDB_TRY(d2h(c, U, ldu, dU, ldA, m, k));
+  RSVDB_TRY(d2h(c, S, k, dS, k, k, 1));
+  RSVDB_TRY(d2h(c, V, ldv, dV, ldN, n, k));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (found) *found = (int)k;
+  return RSVDB_OK;
+}
+
+int rsvdb_qr_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, int full, double* Q, int64_t ldq, double* R,
+                  int64_t ldr) {
+  if (!c || !A || !Q || !R || m <= 0 || n <= 0 || lda < m || ldq < m) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "QR: bad argument");
+  if (!full && m < n) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "reduced QR needs rows >= cols (reference src/QR.cpp:78-79)");
+  if (ldr < (full ? m : n)) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "QR: ldr too small");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t ldA = even_ld(m);
+  if (!full) {
+    const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)n * n)) * 8 + 256;
+    RSVDB_CUDA(c, c->io_ws.reserve(need));
+    IoArena ar(c); double* dA = ar.take((size_t)ldA * n); double* dR = ar.take((size_t)n * n);
+    RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
+    RSVDB_TRY(rsvdb_qr_dev(c, dA, m, (int)n, ldA, 0, dR));
+    k_sign_normalise<<<(unsigned)n, 256, 0, c->stream>>>(dA, ldA, m, dR, n, (int)n, (int)n);
+    RSVDB_CUDA(c, cudaGetLastError()); ++c->launches;
+    RSVDB_TRY(d2h(c, Q, ldq, dA, ldA, m, n));
+    RSVDB_TRY(d2h(c, R, ldr, dR, n, n, n));
+    RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RSVDB_OK;
+  }
+  // full: Q m x m, R m x n
+  const int64_t kk = std::min(m, n);
+  const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)n * n) + IoArena::pad((size_t)ldA * m) +
+                       IoArena::pad((size_t)n) + IoArena::pad((size_t)ldA * n)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  double* dA = ar.take((size_t)ldA * n); double* dRs = ar.take((size_t)n * n); double* dQ = ar.take((size_t)ldA * m);
+  double* dtau = ar.take((size_t)n); double* dRf = ar.take((size_t)ldA * n);
+  RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
+  int nl = 0;
+  RSVDB_CUDA(c, house_full_qr(c->stream, dA, ldA, m, (int)n, dtau, dRs, dQ, ldA, &nl));
+  c->launches += nl;
+  // R (m x n) = [Rs (first min(m,n) rows); 0]
+  RSVDB_CUDA(c, cudaMemsetAsync(dRf, 0, (size_t)ldA * n * 8, c->stream));
+  RSVDB_TRY(copy2d(c, dRs, n, dRf, ldA, kk, (int)n));
+  k_sign_normalise<<<(unsigned)kk, 256, 0, c->stream>>>(dQ, ldA, m, dRf, ldA, (int)n, (int)kk);
+  RSVDB_CUDA(c, cudaGetLastError()); ++c->launches;
+  RSVDB_TRY(d2h(c, Q, ldq, dQ, ldA, m, m));
+  RSVDB_TRY(d2h(c, R, ldr, dRf, ldA, m, n));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_pm_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, uint64_t seed, double* sigma, double* u, double* v) {
+  if (!c || !A || !sigma || !u || !v || m <= 0 || n <= 0 || lda < m) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "PM: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t ldA = even_ld(m), ldN = even_ld(n);
+  const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)ldN * m) + IoArena::pad((size_t)ldA) + IoArena::pad((size_t)ldN) +
+                       IoArena::pad((size_t)std::min(m, n))) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  double* dA = ar.take((size_t)ldA * n); double* dAt = ar.take((size_t)ldN * m); double* du = ar.take((size_t)ldA);
+  double* dv = ar.take((size_t)ldN); double* dS = ar.take((size_t)std::min(m, n));
+  RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
+  RSVDB_TRY(transpose2d(c, dA, ldA, dAt, ldN, m, n));
+  int f = 0;
+  RSVDB_TRY(small_svd_power_t(c, dAt, ldN, m, n, 1, seed, du, ldA, 1, dS, dv, ldN, &f));
+  RSVDB_TRY(d2h(c, u, m, du, ldA, m, 1));
+  RSVDB_TRY(d2h(c, v, n, dv, ldN, n, 1));
+  RSVDB_TRY(d2h(c, sigma, 1, dS, 1, 1, 1));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_gemm_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t ka, int64_t lda, const double* B, int64_t kb, int64_t n,
+                    int64_t ldb, double* C, int64_t ldc) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (ka != kb) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "Matrices dimensions are not compatible for manual matrix multiplication");
+  if (!A || !B || !C || m < 0 || n < 0 || ka < 0 || lda < m || ldb < kb || ldc < m) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "gemm: bad argument");
+  if (m == 0 || n == 0) return RSVDB_OK;
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t ldA = even_ld(m), ldB = even_ld(ka);
+  const size_t need = (IoArena::pad((size_t)ldA * std::max<int64_t>(ka, 1)) + IoArena::pad((size_t)ldB * n) + IoArena::pad((size_t)ldA * n)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  double* dA = ar.take((size_t)ldA * std::max<int64_t>(ka, 1)); double* dB = ar.take((size_t)ldB * n); double* dC = ar.take((size_t)ldA * n);
+  RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, ka));
+  RSVDB_TRY(h2d(c, dB, ldB, B, ldb, ka, n));
+  for (int64_t n0 = 0; n0 < n; n0 += 128) {   // the skinny kernel takes <= 128 columns per launch; wider B goes through in slabs
+    const int nc = (int)std::min<int64_t>(128, n - n0);
+    RSVDB_TRY(rsvdb_gemm_an_dev(c, dA, m, ka, ldA, dB + (size_t)n0 * ldB, ldB, nc, dC + (size_t)n0 * ldA, ldA));
+  }
+  RSVDB_TRY(d2h(c, C, ldc, dC, ldA, m, n));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RSVDB_OK;
 }
 

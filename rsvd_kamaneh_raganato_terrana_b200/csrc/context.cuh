@@ -2,8 +2,11 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <vector>
 #include <cuda_runtime.h>
 #include "gemm_dmma.cuh"
+
+enum RsvdbPhase { PH_GEMM_AN = 0, PH_GEMM_AT = 1, PH_QR = 2, PH_SMALL_SVD = 3, PH_COMM = 4, PH_OTHER = 5, PH_COPY = 6, PH_COUNT = 7 };
 
 struct rsvdb_ctx {
   int device = 0;
@@ -11,15 +14,22 @@ struct rsvdb_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   rsvdb::GemmWorkspace gemm_ws;     // split-K partial tiles
-  rsvdb::GemmWorkspace qr_ws;       // TSQR tree storage
-  rsvdb::GemmWorkspace tmp_ws;      // pipeline intermediates (Y, Z, B, ...)
+  rsvdb::GemmWorkspace qr_ws;       // TSQR tree of the local panel
+  rsvdb::GemmWorkspace qr2_ws;      // TSQR tree of the all-gathered R stack (multi-GPU)
+  rsvdb::GemmWorkspace tmp_ws;      // pipeline intermediates (Q, Z, B^T, small factors)
+  rsvdb::GemmWorkspace svd_ws;      // small-SVD scratch
   rsvdb::GemmWorkspace io_ws;       // device copies for the *_host entry points
-  int launches_i = 0;               // bumped by the launchers
   int64_t launches = 0;
   std::string err;
   // multi-GPU (row-sharded A); comm is an ncclComm_t resolved at run time (comm.cu)
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // optional per-phase device timing (CUDA events on the stream)
+  bool profiling = false;
+  struct Span { int phase; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+  const int* d_svd_info = nullptr;   // device {sweeps, rotations} of the last Jacobi SVD
 };
 
 namespace rsvdb {
@@ -28,12 +38,21 @@ inline int cuda_fail(rsvdb_ctx* c, cudaError_t e, const char* where) {
   if (c) c->err = std::string(where) + ": " + cudaGetErrorString(e);
   return -2;
 }
-struct DeviceGuard {
-  int prev = -1; bool ok;
-  explicit DeviceGuard(int dev) { ok = cudaGetDevice(&prev) == cudaSuccess && (prev == dev || cudaSetDevice(dev) == cudaSuccess); }
-  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+// RAII phase marker: records an event pair around a pipeline phase when profiling is on.
+struct PhaseTimer {
+  rsvdb_ctx* c; int idx = -1;
+  PhaseTimer(rsvdb_ctx* ctx, int phase) : c(ctx) {
+    if (!c->profiling) return;
+    rsvdb_ctx::Span s; s.phase = phase;
+    auto get = [&]() { cudaEvent_t e; if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+    s.a = get(); s.b = get();
+    cudaEventRecord(s.a, c->stream);
+    c->spans.push_back(s); idx = (int)c->spans.size() - 1;
+  }
+  ~PhaseTimer() { if (idx >= 0) cudaEventRecord(c->spans[idx].b, c->stream); }
 };
 }  // namespace rsvdb
 
 #define RSVDB_CUDA(ctx, call)                                              \
   do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return rsvdb::cuda_fail((ctx), e__, #call); } while (0)
+#define RSVDB_TRY(call) do { int rc__ = (call); if (rc__ != 0) return rc__; } while (0)

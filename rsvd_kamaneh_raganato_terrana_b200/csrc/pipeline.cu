@@ -1,0 +1,206 @@
+// Device-side orchestration of the rSVD hot path: range finder, projection, small SVD, back-projection.
+// Mirrors reference src/rSVD.cpp:57-133 step by step; every product and factorisation is one of the sm_100a kernels
+// of this directory, and with c->nranks > 1 the row-sharded variant exchanges only A^T Q partial sums and TSQR R factors.
+#include "pipeline.cuh"
+
+#include <algorithm>
+
+#include "comm.cuh"
+#include "jacobi.cuh"
+#include "tsqr.cuh"
+
+namespace rsvdb {
+
+namespace {
+
+// gathered[p][k][i] (each rank's l x l block, ld = l) -> stack[(p*l + i) + k * (P*l)]
+__global__ void k_restack(const double* __restrict__ gathered, double* __restrict__ stack, int l, int P) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = P * l * l;
+  if (e < total) {
+    const int i = e % l, k = (e / l) % l, p = e / (l * l);
+    stack[(size_t)k * P * l + (size_t)p * l + i] = gathered[e];
+  }
+}
+
+__global__ void k_transpose(const double* __restrict__ src, long long lds, double* __restrict__ dst, long long ldd, int rows, int cols) {
+  // dst (cols x rows) = src (rows x cols)^T
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int cc = threadIdx.y; cc < 32; cc += 8) {
+    const int r = r0 + threadIdx.x, c = c0 + cc;
+    tile[cc][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)c * lds + r] : 0.0;
+  }
+  __syncthreads();
+  for (int rr = threadIdx.y; rr < 32; rr += 8) {
+    const int r = r0 + rr, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(size_t)r * ldd + c] = tile[threadIdx.x][rr];
+  }
+}
+
+__global__ void k_copy2d(const double* __restrict__ src, long long lds, double* __restrict__ dst, long long ldd, long long rows, int cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) for (int k = blockIdx.y; k < cols; k += gridDim.y) dst[(size_t)k * ldd + i] = src[(size_t)k * lds + i];
+}
+
+}  // namespace
+
+int transpose2d(rsvdb_ctx* c, const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows, int64_t cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  dim3 g((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  k_transpose<<<g, dim3(32, 8), 0, c->stream>>>(src, lds, dst, ldd, (int)rows, (int)cols);
+  RSVDB_CUDA(c, cudaGetLastError());
+  ++c->launches;
+  return 0;
+}
+
+int copy2d(rsvdb_ctx* c, const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows, int cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  dim3 g((unsigned)((rows + 255) / 256), (unsigned)std::min(cols, 128));
+  k_copy2d<<<g, 256, 0, c->stream>>>(src, lds, dst, ldd, rows, cols);
+  RSVDB_CUDA(c, cudaGetLastError());
+  ++c->launches;
+  return 0;
+}
+
+int qr_inplace(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bool sharded, const double** R) {
+  PhaseTimer pt(c, PH_QR);
+  int k = 0;
+  Tsqr t(&c->qr_ws);
+  RSVDB_CUDA(c, t.plan(rows, l));
+  RSVDB_CUDA(c, t.factor(c->stream, Y, ldy, &k));
+  const bool dist = sharded && c->nranks > 1;
+  if (!dist) {
+    RSVDB_CUDA(c, t.form_q(c->stream, Y, ldy, nullptr, 0, &k));
+    if (R) *R = t.R_local();
+    c->launches += k;
+    return 0;
+  }
+  // TSQR over row shards: all-gather the l x l R factors, factor the (P*l) x l stack redundantly on every rank
+  // (deterministic kernels => identical bits), and push this rank's l x l block of the stack's Q down the local tree.
+  const int P = c->nranks;
+  Tsqr t2(&c->qr2_ws);
+  RSVDB_CUDA(c, t2.plan((long long)P * l, l));
+  // scratch behind t2's own storage: gathered blocks + the stack
+  const size_t extra = (size_t)2 * P * l * l * sizeof(double);
+  GemmWorkspace& gw = c->svd_ws;
+  RSVDB_CUDA(c, gw.reserve(extra));
+  double* gathered = gw.ptr; double* stack = gw.ptr + (size_t)P * l * l;
+  {
+    PhaseTimer pc(c, PH_COMM);
+    RSVDB_TRY(comm_allgather(c, t.R_local(), gathered, (size_t)l * l));
+  }
+  k_restack<<<(P * l * l + 255) / 256, 256, 0, c->stream>>>(gathered, stack, l, P);
+  RSVDB_CUDA(c, cudaGetLastError()); ++k;
+  RSVDB_CUDA(c, t2.factor(c->stream, stack, (long long)P * l, &k));
+  RSVDB_CUDA(c, t2.form_q(c->stream, stack, (long long)P * l, nullptr, 0, &k));
+  RSVDB_CUDA(c, t.form_q(c->stream, Y, ldy, stack + (size_t)c->rank * l, (long long)P * l, &k));
+  if (R) *R = t2.R_local();
+  c->launches += k;
+  return 0;
+}
+
+static int gemm_an_phase(rsvdb_ctx* c, const double* A, int64_t M, int64_t K, int64_t lda, const double* X, int64_t ldx, int N,
+                         double* Y, int64_t ldy) {
+  PhaseTimer pt(c, PH_GEMM_AN);
+  int k = 0;
+  RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, A, M, K, lda, X, ldx, N, Y, ldy, &k));
+  c->launches += k;
+  return 0;
+}
+static int gemm_at_phase(rsvdb_ctx* c, const double* A, int64_t K, int64_t M, int64_t lda, const double* Q, int64_t ldq, int N,
+                         double* Z, int64_t ldz, int transpose_out, bool reduce) {
+  {
+    PhaseTimer pt(c, PH_GEMM_AT);
+    int k = 0;
+    RSVDB_CUDA(c, gemm_at(c->gemm_ws, c->stream, c->nsm, A, K, M, lda, Q, ldq, N, Z, ldz, transpose_out, &k));
+    c->launches += k;
+  }
+  if (reduce && c->nranks > 1) {
+    // A^T Q = sum over row shards of A_p^T Q_p; Z is contiguous (ldz == M or N) by construction in this file
+    PhaseTimer pc(c, PH_COMM);
+    RSVDB_TRY(comm_allreduce_sum(c, Z, (size_t)M * N));
+  }
+  return 0;
+}
+
+int range_finder(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
+                 int l, int q, double* Q, int64_t ldq) {
+  if (l <= 0 || q < 0) return fail(c, -1, "range_finder: l must be positive and q non-negative");
+  // Z (n x l) lives in tmp_ws at offset 0
+  RSVDB_CUDA(c, c->tmp_ws.reserve(std::max<size_t>(c->tmp_ws.bytes, (size_t)n * l * sizeof(double))));
+  double* Z = c->tmp_ws.ptr;
+  RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Omega, ldo, l, Q, ldq));            // Y = A * Omega          src/rSVD.cpp:59
+  RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));                       // Q = qr(Y).Q            :60-61
+  for (int it = 0; it < q; ++it) {                                             // :62
+    RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, ldq, l, Z, n, 0, true));       // Y = A^T * Q            :63
+    RSVDB_TRY(qr_inplace(c, Z, n, l, n, false, nullptr));                      // Q = qr(Y).Q  (n x l)   :64-65
+    RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Z, n, l, Q, ldq));                // Y = A * Q              :66
+    RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));                     // Q = qr(Y).Q            :67-68
+  }
+  return 0;
+}
+
+int small_svd_jacobi(rsvdb_ctx* c, const double* M, int64_t ldm, const double* Mt, int64_t ldmt, int64_t r, int64_t cd,
+                     double* U, int64_t ldu, double* S, double* V, int64_t ldv) {
+  PhaseTimer pt(c, PH_SMALL_SVD);
+  const int64_t k = std::min(r, cd);
+  if (k <= 0) return 0;
+  if (k > 512) return fail(c, -6, "small SVD: min(rows, cols) > 512 is not supported");
+  int nl = 0;
+  // scratch: tall copy (max(r,cd) x k), Uw (k x k), Zw (k x k), info
+  const int64_t tall = std::max(r, cd);
+  const size_t need = ((size_t)tall * k + 2 * (size_t)k * k + 16) * sizeof(double);
+  RSVDB_CUDA(c, c->svd_ws.reserve(need));
+  double* T = c->svd_ws.ptr; double* Uw = T + (size_t)tall * k; double* Zw = Uw + (size_t)k * k;
+  int* info = reinterpret_cast<int*>(Zw + (size_t)k * k);
+  GemmWorkspace& jws = c->qr2_ws;   // global-memory Jacobi scratch for k > ~116 (qr2_ws is idle here)
+  if (r == cd) {
+    // no preconditioner (include/SVD_class.hpp:110-123 takes neither branch)
+    const double* W = M ? M : Mt; const int64_t ldw = M ? ldm : ldmt;
+    RSVDB_CUDA(c, jacobi_svd_square(jws, c->stream, W, ldw, (int)k, M ? 0 : 1, U, ldu, S, V, ldv, info, &nl));
+  } else if (r > cd) {
+    // QR(M) -> work = R (c x c), U = Q_M * Uw, V = Zw                     (:110-115)
+    if (M) { RSVDB_TRY(copy2d(c, M, ldm, T, r, r, (int)cd)); }
+    else { RSVDB_TRY(transpose2d(c, Mt, ldmt, T, r, cd, r)); }
+    const double* R = nullptr;
+    RSVDB_TRY(qr_inplace(c, T, r, (int)cd, r, false, &R));
+    RSVDB_CUDA(c, jacobi_svd_square(jws, c->stream, R, cd, (int)k, 0, Uw, k, S, V, ldv, info, &nl));
+    RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, T, r, k, r, Uw, k, (int)k, U, ldu, &nl));
+  } else {
+    // QR(M^T) -> work = R^T (r x r), U = Uw, V = Q_{M^T} * Zw              (:116-123)
+    if (Mt) { RSVDB_TRY(copy2d(c, Mt, ldmt, T, cd, cd, (int)r)); }
+    else { RSVDB_TRY(transpose2d(c, M, ldm, T, cd, r, cd)); }
+    const double* R = nullptr;
+    RSVDB_TRY(qr_inplace(c, T, cd, (int)r, cd, false, &R));
+    RSVDB_CUDA(c, jacobi_svd_square(jws, c->stream, R, r, (int)k, 1, U, ldu, S, Zw, k, info, &nl));
+    RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, T, cd, k, cd, Zw, k, (int)k, V, ldv, &nl));
+  }
+  c->launches += nl;
+  c->d_svd_info = info;   // sweeps / rotations are fetched lazily by rsvdb_last_svd_info()
+  return 0;
+}
+
+int rsvd_device(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
+                int l, int q, int method, double* U, int64_t ldu, double* S, double* V, int64_t ldv, uint64_t seed) {
+  if (method != 0 && method != 1 && method != 2) return fail(c, -1, "Unsupported SVD method");   // src/rSVD.cpp:122-123
+  if (l <= 0 || n <= 0 || m < 0) return fail(c, -1, "rSVD: bad shape");
+  const int64_t k = std::min<int64_t>(l, n);
+  // tmp_ws layout: [Z / Bt : n x l][Q : m x l][Ut : l x k]
+  const size_t need = ((size_t)n * l + (size_t)m * l + (size_t)l * l + 64) * sizeof(double);
+  RSVDB_CUDA(c, c->tmp_ws.reserve(need));
+  double* Bt = c->tmp_ws.ptr;
+  double* Q = Bt + (size_t)n * l;
+  double* Ut = Q + (size_t)m * l;
+  RSVDB_TRY(range_finder(c, A, m, n, lda, Omega, ldo, l, q, Q, m));                 // Stage A          src/rSVD.cpp:84-85
+  RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, m, l, Bt, n, 0, true));               // B^T = A^T Q      :89 (stored transposed)
+  if (method == 1) {
+    RSVDB_TRY(small_svd_power_t(c, Bt, n, l, n, 0, seed, Ut, l, l, S, V, ldv, nullptr));   // SVD<Power>(B)    :105-112
+  } else {
+    RSVDB_TRY(small_svd_jacobi(c, nullptr, 0, Bt, n, l, n, Ut, l, S, V, ldv));       // SVD<method>(B)   :96-121
+  }
+  RSVDB_TRY(gemm_an_phase(c, Q, m, l, m, Ut, l, (int)k, U, ldu));                   // U = Q * Utilde   :128
+  return 0;
+}
+
+}  // namespace rsvdb

@@ -1,0 +1,247 @@
+"""Host-side mirror of the reference's rSVD API, in Python, over the C ABI of librsvdb.so.
+
+The reference is C++ (Eigen types); its maintainers would use the C++ drop-in headers under include/.  This module is
+the same surface for Python callers and for the parity tests, with the reference's names and argument meaning:
+
+    rSVD(A, l, method)                 include/rSVD.hpp:14      -> (U, S, V)
+    intermediate_step(A, Omega, l, q)  include/rSVD.hpp:13      -> Q
+    generateOmega(n, l)                include/rSVD.hpp:15      -> Omega
+    SVD(method)(A, r).compute()        include/SVD_class.hpp:35 -> getU / getS / getV
+    qr_decomposition_reduced / _full   include/QR.hpp:15-16     -> (Q, R)
+    PM(A)                              include/PM.hpp:18        -> (sigma, u, v)
+    manualMatrixMultiply(A, B)         include/matrixOperations.hpp:14
+
+Host arrays are numpy float64 (any layout; they are passed column-major like Eigen::MatrixXd).  All arithmetic runs in
+the CUDA library; nothing here computes on the CPU and there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from enum import IntEnum
+
+import numpy as np
+
+from . import capi
+
+
+class SVDMethod(IntEnum):
+    """enum class SVDMethod -- include/SVD_class.hpp:28-32."""
+    Jacobi = 0
+    Power = 1
+    ParallelJacobi = 2
+
+
+def _f(a) -> np.ndarray:
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+class Engine:
+    """One librsvdb context (one GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = capi.load()
+        h = ctypes.c_void_p()
+        rc = self.lib.rsvdb_create(ctypes.byref(h), device)
+        if rc != 0:
+            raise capi.RsvdbError(rc, "rsvdb_create failed (is a B200 / sm_100 GPU visible?)")
+        self.h = h
+        self.device = device
+
+    # -- plumbing -------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rsvdb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self.lib.rsvdb_last_error(self.h).decode()
+            if rc == capi.ERR_INVALID_ARGUMENT:
+                raise ValueError(msg)          # the reference throws std::invalid_argument
+            raise capi.RsvdbError(rc, msg)
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.rsvdb_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.rsvdb_synchronize(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.rsvdb_launch_count(self.h))
+
+    def set_profiling(self, on: bool):
+        self._check(self.lib.rsvdb_set_profiling(self.h, int(on)))
+
+    def phase_ms(self) -> dict:
+        out = (ctypes.c_double * 7)()
+        self._check(self.lib.rsvdb_phase_ms(self.h, out))
+        names = ["gemm_an", "gemm_at", "tsqr", "small_svd", "comm", "other", "copy"]
+        return dict(zip(names, [float(x) for x in out]))
+
+    def last_svd_info(self):
+        s = ctypes.c_int(); r = ctypes.c_int()
+        self._check(self.lib.rsvdb_last_svd_info(self.h, ctypes.byref(s), ctypes.byref(r)))
+        return s.value, r.value
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        buf = ctypes.create_string_buffer(uid, 128)
+        self._check(self.lib.rsvdb_comm_init(self.h, nranks, rank, ctypes.cast(buf, ctypes.c_void_p)))
+
+    def comm_unique_id(self) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        rc = self.lib.rsvdb_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p))
+        if rc != 0:
+            raise capi.RsvdbError(rc, "ncclGetUniqueId failed")
+        return buf.raw
+
+    # -- reference API mirrors (host arrays) --------------------------------------------------------------------------
+    def generateOmega(self, n: int, l: int, seed: int = 0) -> np.ndarray:
+        """src/rSVD.cpp:12-55 (N(0,1) entries; seeded here, std::random_device there)."""
+        Om = np.zeros((n, l), order="F")
+        self._check(self.lib.rsvdb_generate_omega_host(self.h, n, l, seed, _ptr(Om), max(n, 1)))
+        return Om
+
+    def intermediate_step(self, A, Omega, l: int, q: int) -> np.ndarray:
+        """src/rSVD.cpp:57-70."""
+        A = _f(A); Omega = _f(Omega); m, n = A.shape
+        if Omega.shape != (n, l):
+            raise ValueError("Omega must be n x l")
+        Q = np.zeros((m, l), order="F")
+        self._check(self.lib.rsvdb_intermediate_step_host(self.h, _ptr(A), m, n, max(m, 1), _ptr(Omega), n, l, q, _ptr(Q), max(m, 1)))
+        return Q
+
+    def rSVD(self, A, l: int, method=SVDMethod.Jacobi, Omega=None, q: int = 2, seed: int = 0):
+        """rSVD(A, U, S, V, l, method) -- src/rSVD.cpp:72-133.  Returns (U, S, V) with the reference's output shapes:
+        Jacobi / ParallelJacobi: U m x k, S k, V n x k;  Power: U m x l, S l, V n x n with the vectors in ROWS."""
+        A = _f(A); m, n = A.shape
+        try:
+            method = int(method)
+        except Exception as e:
+            raise ValueError("Unsupported SVD method") from e
+        k = min(l, n)
+        U = np.zeros((m, max(k, 1)), order="F"); S = np.zeros(max(k, 1)); V = np.zeros((n, max(k, 1)), order="F")
+        om_ptr, ldo = None, 0
+        if Omega is not None:
+            Omega = _f(Omega)
+            if Omega.shape != (n, l):
+                raise ValueError("Omega must be n x l")
+            om_ptr, ldo = _ptr(Omega), n
+        self._check(self.lib.rsvdb_rsvd_host(self.h, _ptr(A), m, n, max(m, 1), om_ptr, ldo, seed, l, q, method,
+                                             _ptr(U), max(m, 1), _ptr(S), _ptr(V), n))
+        if method == SVDMethod.Power:
+            return U, S, _power_v_layout(V, n, k, k)
+        return U, S, V
+
+    def qr_decomposition_reduced(self, A):
+        """src/QR.cpp:43-80: Q m x n, R n x n."""
+        A = _f(A); m, n = A.shape
+        Q = np.zeros((m, n), order="F"); R = np.zeros((n, n), order="F")
+        self._check(self.lib.rsvdb_qr_host(self.h, _ptr(A), m, n, m, 0, _ptr(Q), m, _ptr(R), n))
+        return Q, R
+
+    def qr_decomposition_full(self, A):
+        """src/QR.cpp:22-41: Q m x m, R m x n."""
+        A = _f(A); m, n = A.shape
+        Q = np.zeros((m, m), order="F"); R = np.zeros((m, n), order="F")
+        self._check(self.lib.rsvdb_qr_host(self.h, _ptr(A), m, n, m, 1, _ptr(Q), m, _ptr(R), m))
+        return Q, R
+
+    def PM(self, A, seed: int = 0):
+        """PM(A, B, sigma, u, v) -- src/PM.cpp:4-81."""
+        A = _f(A); m, n = A.shape
+        u = np.zeros(m); v = np.zeros(n); sigma = ctypes.c_double()
+        self._check(self.lib.rsvdb_pm_host(self.h, _ptr(A), m, n, m, seed, ctypes.byref(sigma), _ptr(u), _ptr(v)))
+        return sigma.value, u, v
+
+    def manualMatrixMultiply(self, A, B):
+        """src/matrixOperations.cpp:7-28."""
+        A = _f(A); B = _f(B)
+        C = np.zeros((A.shape[0], B.shape[1]), order="F")
+        self._check(self.lib.rsvdb_gemm_host(self.h, _ptr(A), A.shape[0], A.shape[1], max(A.shape[0], 1), _ptr(B), B.shape[0],
+                                             B.shape[1], max(B.shape[0], 1), _ptr(C), max(A.shape[0], 1)))
+        return C
+
+    def svd(self, A, method=SVDMethod.Jacobi, r: int = 0, seed: int = 0):
+        """SVD<method>(A, r).compute() -- include/SVD_class.hpp:79-97.  Returns (U, S, V) in the reference's shapes."""
+        A = _f(A); m, n = A.shape; k = min(m, n)
+        try:
+            method = int(method)
+        except Exception as e:
+            raise ValueError("Unsupported SVD method") from e
+        found = ctypes.c_int()
+        if method == SVDMethod.Power:
+            dim = r if r else k
+            U = np.zeros((m, m), order="F"); S = np.zeros(k); V = np.zeros((n, max(dim, 1)), order="F")
+            self._check(self.lib.rsvdb_svd_host(self.h, _ptr(A), m, n, m, method, r, seed, _ptr(U), m, _ptr(S), _ptr(V), n, ctypes.byref(found)))
+            f = found.value
+            Vref = _power_v_layout(V, n, dim, f)
+            if f < dim:   # conservativeResize on the early exit, include/SVD_class.hpp:198-209
+                if f == 0:
+                    return np.zeros((m, 1), order="F"), np.zeros(1), np.zeros((n, 1), order="F")
+                return _f(U[:, :f]), S[:f].copy(), _f(Vref[:, :f])
+            return U, S, Vref
+        U = np.zeros((m, k), order="F"); S = np.zeros(k); V = np.zeros((n, k), order="F")
+        self._check(self.lib.rsvdb_svd_host(self.h, _ptr(A), m, n, m, method, r, seed, _ptr(U), m, _ptr(S), _ptr(V), n, ctypes.byref(found)))
+        return U, S, V
+
+
+def _power_v_layout(Vcols: np.ndarray, n: int, dim: int, found: int) -> np.ndarray:
+    """The Power back-end stores right singular vectors in the ROWS of an identity-initialised n x n matrix
+    (include/SVD_class.hpp:83,214)."""
+    V = np.asfortranarray(np.eye(n))
+    for i in range(min(found, dim)):
+        V[i, :] = Vcols[:, i]
+    return V
+
+
+class SVD:
+    """template<SVDMethod> class SVD -- include/SVD_class.hpp:35-71."""
+
+    def __init__(self, engine: Engine, method, data, r: int = 0, seed: int = 0):
+        self._e, self._method, self._r, self._seed = engine, method, r, seed
+        self._data = _f(data).copy(order="F")        # the reference copies its input (data_, :55,74-75)
+        self._U = self._S = self._V = None
+
+    def setData(self, data):                           # protected in the reference (:67-70), used by PCA
+        self._data = _f(data).copy(order="F")
+
+    def compute(self):
+        self._U, self._S, self._V = self._e.svd(self._data, self._method, self._r, self._seed)
+
+    def getU(self): return self._U.copy(order="F")     # getters return by value (:46-48)
+    def getS(self): return self._S.copy()
+    def getV(self): return self._V.copy(order="F")
+
+
+_default = None
+
+
+def default_engine() -> Engine:
+    global _default
+    if _default is None:
+        _default = Engine(0)
+    return _default
+
+
+# free functions with the reference's names
+def rSVD(A, l, method=SVDMethod.Jacobi, Omega=None, q=2, seed=0):
+    return default_engine().rSVD(A, l, method, Omega, q, seed)
+
+
+def intermediate_step(A, Omega, l, q):
+    return default_engine().intermediate_step(A, Omega, l, q)
+
+
+def generateOmega(n, l, seed=0):
+    return default_engine().generateOmega(n, l, seed)
