@@ -44,13 +44,21 @@ inline int64_t even_ld(int64_t rows) { return std::max<int64_t>(2, (rows + 1) & 
 int h2d(rsvdb_ctx* c, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
   if (rows <= 0 || cols <= 0) return 0;
   PhaseTimer pt(c, PH_COPY);
-  RSVDB_CUDA(c, cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyHostToDevice, c->stream));
+  if (ldd == rows && lds == rows) {
+    RSVDB_CUDA(c, cudaMemcpyAsync(dst, src, (size_t)rows * cols * 8, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    RSVDB_CUDA(c, cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyHostToDevice, c->stream));
+  }
   return 0;
 }
 int d2h(rsvdb_ctx* c, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
   if (rows <= 0 || cols <= 0) return 0;
   PhaseTimer pt(c, PH_COPY);
-  RSVDB_CUDA(c, cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyDeviceToHost, c->stream));
+  if (ldd == rows && lds == rows) {
+    RSVDB_CUDA(c, cudaMemcpyAsync(dst, src, (size_t)rows * cols * 8, cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    RSVDB_CUDA(c, cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyDeviceToHost, c->stream));
+  }
   return 0;
 }
 

@@ -199,7 +199,12 @@ int rsvd_device(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda
   } else {
     RSVDB_TRY(small_svd_jacobi(c, nullptr, 0, Bt, n, l, n, Ut, l, S, V, ldv));       // SVD<method>(B)   :96-121
   }
-  RSVDB_TRY(gemm_an_phase(c, Q, m, l, m, Ut, l, (int)k, U, ldu));                   // U = Q * Utilde   :128
+  {
+    PhaseTimer pt(c, PH_OTHER);                                                      // U = Q * Utilde   :128
+    int nl = 0;
+    RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, Q, m, l, m, Ut, l, (int)k, U, ldu, &nl));
+    c->launches += nl;
+  }
   return 0;
 }
 

@@ -105,6 +105,29 @@ class Engine:
             raise capi.RsvdbError(rc, "ncclGetUniqueId failed")
         return buf.raw
 
+    # -- device-pointer entry points (raw addresses; the caller owns the memory, e.g. torch tensors) ------------------------
+    def gemm_an_dev(self, dA, m, n, lda, dX, ldx, l, dY, ldy):
+        self._check(self.lib.rsvdb_gemm_an_dev(self.h, dA, m, n, lda, dX, ldx, l, dY, ldy))
+
+    def gemm_at_dev(self, dA, m, n, lda, dQ, ldq, l, dZ, ldz, transpose_out=False):
+        self._check(self.lib.rsvdb_gemm_at_dev(self.h, dA, m, n, lda, dQ, ldq, l, dZ, ldz, int(transpose_out)))
+
+    def qr_dev(self, dY, rows, l, ldy, sharded=False, dR=None):
+        self._check(self.lib.rsvdb_qr_dev(self.h, dY, rows, l, ldy, int(sharded), dR))
+
+    def range_finder_dev(self, dA, m_local, n, lda, dOmega, ldo, l, q, dQ, ldq):
+        self._check(self.lib.rsvdb_range_finder_dev(self.h, dA, m_local, n, lda, dOmega, ldo, l, q, dQ, ldq))
+
+    def rsvd_dev(self, dA, m_local, n, lda, dOmega, ldo, l, q, method, dU, ldu, dS, dV, ldv, seed=0):
+        self._check(self.lib.rsvdb_rsvd_dev(self.h, dA, m_local, n, lda, dOmega, ldo, l, q, int(method), seed, dU, ldu, dS, dV, ldv))
+
+    def generate_omega_dev(self, n, l, seed, dOmega, ldo):
+        self._check(self.lib.rsvdb_generate_omega_dev(self.h, n, l, seed, dOmega, ldo))
+
+    def rsvd_host_raw(self, pA, m, n, lda, pOmega, ldo, seed, l, q, method, pU, ldu, pS, pV, ldv):
+        """rsvdb_rsvd_host on raw host addresses (e.g. pinned torch tensors)."""
+        self._check(self.lib.rsvdb_rsvd_host(self.h, pA, m, n, lda, pOmega, ldo, seed, l, q, int(method), pU, ldu, pS, pV, ldv))
+
     # -- reference API mirrors (host arrays) --------------------------------------------------------------------------
     def generateOmega(self, n: int, l: int, seed: int = 0) -> np.ndarray:
         """src/rSVD.cpp:12-55 (N(0,1) entries; seeded here, std::random_device there)."""

@@ -1,0 +1,80 @@
+"""Generates tests/golden/ref_outputs.npz from the reference's OWN first-party sources, compiled over the Eigen/MPI
+stand-in by oracle/Makefile (oracle/_ref/libref_rsvd.so).  Run in the dev container, where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+The fixtures are what the -m "not gpu" tests pin the oracle against, and what the -m gpu tests compare the CUDA path
+with, on boxes where /root/reference is absent.  Inputs are regenerated from seeds (workloads.py), only outputs are stored.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import rsvd_oracle as O  # noqa: E402
+from rsvd_kamaneh_raganato_terrana_b200 import workloads as W  # noqa: E402
+
+
+def small_inputs():
+    """Seeded small matrices for the SVD / QR back-ends (name -> matrix)."""
+    rng = np.random.default_rng(20260101)
+    d = {
+        "gauss_16x100": rng.standard_normal((16, 100)),
+        "gauss_64x64": rng.standard_normal((64, 64)),
+        "gauss_100x30": rng.standard_normal((100, 30)),
+        "gauss_50x300": rng.standard_normal((50, 300)),
+        "decay_40x40": rng.standard_normal((40, 40)) @ np.diag(0.5 ** np.arange(40)) @ rng.standard_normal((40, 40)),
+        "diag_1_to_100": np.diag(np.arange(1.0, 101.0)),                      # image_compression/data/input/mat: sigma = sorted |diag|
+        "qr_test2_4x3": np.arange(1.0, 13.0).reshape(4, 3),                  # image_compression/tests/QR_test2.cpp:24-29
+    }
+    return {k: np.asfortranarray(v) for k, v in d.items()}
+
+
+def rsvd_inputs():
+    rng = np.random.default_rng(20260102)
+    d = {nm: (gen(), W.C1_L) for nm, gen in W.C1_CASES}                      # tests/rSVD_test.cpp on input/*.mtx, l = 16
+    d["decay_300x120"] = (np.asfortranarray(rng.standard_normal((300, 120)) @ np.diag(0.8 ** np.arange(120)) @ rng.standard_normal((120, 120))), 20)
+    d["uniform_250x250"] = (np.asfortranarray(rng.uniform(-1, 1, (250, 250))), 50)   # tests/rSVD_test2.cpp shape, l = 50
+    d["pod_2000x300"] = (W.c4_pod(2000, 300), 32)
+    return d
+
+
+def main():
+    ref = O.RefLib()
+    out = {}
+    for nm, (A, l) in rsvd_inputs().items():
+        Om = W.omega(A.shape[1], l)
+        Q = ref.intermediate_step(A, Om, l, 2)
+        out[f"istep/{nm}/Q"] = Q
+        for meth, tag in ((O.JACOBI, "jacobi"), (O.PARALLEL_JACOBI, "pjacobi")):
+            U, S, V = ref.rsvd(A, Om, l, meth)
+            out[f"rsvd/{nm}/{tag}/S"] = S
+            out[f"rsvd/{nm}/{tag}/err"] = np.array(O.reconstruction_error(A, U, S, V))
+            out[f"rsvd/{nm}/{tag}/U"] = U
+            out[f"rsvd/{nm}/{tag}/Vshape"] = np.array(V.shape)
+    for nm, B in small_inputs().items():
+        for meth, tag in ((O.JACOBI, "jacobi"), (O.PARALLEL_JACOBI, "pjacobi")):
+            U, S, V = ref.svd(B, meth)
+            out[f"svd/{nm}/{tag}/S"] = S
+            out[f"svd/{nm}/{tag}/shapes"] = np.array(list(U.shape) + list(V.shape))
+        if B.shape[0] >= B.shape[1]:
+            Q, R = ref.qr_reduced(B)
+            out[f"qr/{nm}/absR"] = np.abs(R)
+            out[f"qr/{nm}/diagR"] = np.diag(R).copy()
+    # scalar helpers
+    rng = np.random.default_rng(7)
+    xyz = rng.standard_normal((20, 3)); xyz[3] = [1.0, 0.0, 2.0]
+    out["make_jacobi/in"] = xyz
+    out["make_jacobi/out"] = np.array([[float(ok), c, s] for ok, c, s in (ref.make_jacobi(*row) for row in xyz)])
+    M = rng.standard_normal((10, 2, 2))
+    out["svd2x2/in"] = M
+    out["svd2x2/out"] = np.array([ref.real_2x2_jacobi_svd(m) for m in M])
+    out["pm_iterations"] = np.array([[n, O.pm_iterations(n)] for n in (100, 1000, 2000, 4096, 20000)])
+    np.savez_compressed(Path(__file__).with_name("ref_outputs.npz"), **out)
+    print("wrote", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,33 @@
+"""TEST INFRASTRUCTURE: numpy + torch.distributed model of the row-sharded rSVD, rank for rank the communication pattern
+of rsvd_kamaneh_raganato_terrana_b200/csrc/pipeline.cu (qr_inplace's sharded branch and gemm_at_phase's all-reduce)."""
+import numpy as np
+
+
+def _allreduce(x, dist, torch):
+    t = torch.from_numpy(np.ascontiguousarray(x)); dist.all_reduce(t); return t.numpy()
+
+
+def _allgather(x, dist, torch):
+    t = torch.from_numpy(np.ascontiguousarray(x)); out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t); return [o.numpy() for o in out]
+
+
+def tsqr_sharded(Y_p, dist, torch, O):
+    """local Householder QR -> all-gather R_p -> QR of the stacked R's on every rank -> Q_p = Q_local * Q_stack[p block]."""
+    l = Y_p.shape[1]
+    Q1, R1 = O.householder_qr(Y_p)
+    stack = np.vstack(_allgather(R1, dist, torch))
+    Q2, R = O.householder_qr(stack)
+    p = dist.get_rank()
+    return Q1 @ Q2[p * l:(p + 1) * l, :], R
+
+
+def rsvd_sharded(A_p, Omega, l, q, dist, torch, O):
+    Q_p, _ = tsqr_sharded(A_p @ Omega, dist, torch, O)                 # shard-local product, distributed QR
+    for _ in range(q):
+        Z = _allreduce(A_p.T @ Q_p, dist, torch)                        # n x l partial sums
+        Qz, _ = O.householder_qr(Z)                                     # replicated
+        Q_p, _ = tsqr_sharded(A_p @ Qz, dist, torch, O)
+    Bt = _allreduce(A_p.T @ Q_p, dist, torch)                           # B^T = A^T Q
+    Ut, S, V, _ = O.svd_jacobi(Bt.T)                                    # replicated small SVD
+    return Q_p @ Ut, S, V

@@ -1,0 +1,53 @@
+"""CPU tests of the drop-in boundary: librsvdb.so loads, exports every symbol include/rsvdb.h declares, and refuses to
+run without a GPU (no CPU fallback)."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from rsvd_kamaneh_raganato_terrana_b200 import capi
+    lib = capi.load()
+    declared = capi.exported_symbols()
+    assert len(declared) >= 29
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/rsvdb.h but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", str(capi.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (rsvdb_\w+)", out))
+    assert exported == set(declared)
+    assert lib.rsvdb_version().startswith(b"rsvdb")
+    assert lib.rsvdb_pm_iterations(100) == 148 and lib.rsvdb_pm_iterations(20000) == 151   # reference src/PM.cpp:25-28
+
+
+def test_header_is_plain_c():
+    """include/rsvdb.h must compile as C (extern "C", plain pointers and sizes, no C++ or torch types)."""
+    src = ROOT / "build" / "hdr_check.c"
+    src.parent.mkdir(exist_ok=True)
+    src.write_text('#include "rsvdb.h"\nint main(void){ return (int)sizeof(rsvdb_status) * 0; }\n')
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Werror", "-I", str(ROOT / "include"), "-fsyntax-only", str(src)], check=True)
+
+
+def test_no_cpu_fallback():
+    import torch
+    from rsvd_kamaneh_raganato_terrana_b200 import capi, Engine
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible; the refusal path is exercised on the CPU box")
+    lib = capi.load()
+    h = ctypes.c_void_p()
+    assert lib.rsvdb_create(ctypes.byref(h), 0) == capi.ERR_CUDA
+    with pytest.raises(capi.RsvdbError):
+        Engine(0)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing in the product package may import, load or link it."""
+    pkg = ROOT / "rsvd_kamaneh_raganato_terrana_b200"
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list((ROOT / "include").glob("*")):
+        text = p.read_text()
+        for pat in (r"^\s*(from|import)\s+oracle", r"rsvd_oracle", r"liboracle", r"libref_rsvd", r"oracle/", r"oracle_c"):
+            assert not re.search(pat, text, flags=re.M), f"{p} reaches into the oracle ({pat})"

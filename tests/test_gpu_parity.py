@@ -1,0 +1,292 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (librsvdb.so), against the CPU oracle on the same seeded
+inputs, against the golden vectors produced by the reference's own sources (tests/golden/ref_outputs.npz), and -- at
+BASELINE.json's full size -- through size-independent properties.
+
+Tolerances (north_star / SURVEY.md 8d):
+  singular values   |s - s_ref| <= 1e-8 * max(s_ref, 1e-6 * s_ref[0])
+  subspace          sin(theta_max) <= 1e-6 on the numerically non-zero part, when a gap follows it
+  reconstruction    ||A - U S V^T||_F <= oracle's + 1e-8 ||A||_F   (one-sided: the reference's ParallelJacobi / Power
+                    back-ends are themselves only 1e-7..1e-4 accurate)
+  orthogonality     ||U^T U - I||_F, ||V^T V - I||_F <= 1e-10
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+import make_golden as G  # noqa: E402
+from rsvd_kamaneh_raganato_terrana_b200 import SVDMethod, SVD, workloads as W  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(Path(__file__).resolve().parent / "golden" / "ref_outputs.npz")
+SIGMA_RTOL, SIGMA_FLOOR, SIN_TOL, REC_TOL, ORTH_TOL = 1e-8, 1e-6, 1e-6, 1e-8, 1e-10
+
+
+def sigma_ok(S, Sref):
+    return np.all(np.abs(S - Sref) <= SIGMA_RTOL * np.maximum(Sref, SIGMA_FLOOR * Sref[0]))
+
+
+def check_rsvd(oracle, A, Ug, Sg, Vg, Uo, So, Vo, l, two_sided=True):
+    nA = np.linalg.norm(A)
+    assert Ug.shape == Uo.shape and Vg.shape == Vo.shape and Sg.shape == So.shape
+    assert sigma_ok(Sg, So)
+    eg, eo = oracle.reconstruction_error(A, Ug, Sg, Vg), oracle.reconstruction_error(A, Uo, So, Vo)
+    assert eg <= eo + REC_TOL * nA
+    if two_sided:
+        assert eo <= eg + REC_TOL * nA
+    assert np.linalg.norm(Ug.T @ Ug - np.eye(Ug.shape[1])) <= ORTH_TOL
+    assert np.linalg.norm(Vg.T @ Vg - np.eye(Vg.shape[1])) <= ORTH_TOL
+    r = int(np.sum(So >= SIGMA_FLOOR * So[0]))
+    if r == len(So) or So[r] < 1e-3 * So[r - 1]:
+        assert oracle.subspace_sin_theta(Uo[:, :r], Ug[:, :r]) <= SIN_TOL
+        assert oracle.subspace_sin_theta(Vo[:, :r], Vg[:, :r]) <= SIN_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# config 1 and friends: rSVD against the oracle and against the reference's own outputs
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(G.rsvd_inputs().keys()))
+def test_rsvd_vs_oracle_and_reference_golden(engine, oracle, name):
+    A, l = G.rsvd_inputs()[name]
+    Om = W.omega(A.shape[1], l)
+    Qg = engine.intermediate_step(A, Om, l, 2)
+    assert np.linalg.norm(Qg.T @ Qg - np.eye(l)) <= ORTH_TOL
+    Uo, So, Vo = oracle.rsvd(A, Om, l, 2, oracle.JACOBI)
+    for meth, tag in ((SVDMethod.Jacobi, "jacobi"), (SVDMethod.ParallelJacobi, "pjacobi")):
+        Ug, Sg, Vg = engine.rSVD(A, l, meth, Omega=Om, q=2)
+        # oracle: the Jacobi restatement (the ParallelJacobi one is looser than the tolerance, see module docstring)
+        check_rsvd(oracle, A, Ug, Sg, Vg, Uo, So, Vo, l, two_sided=True)
+        # reference's own sources
+        Sref = GOLD[f"rsvd/{name}/jacobi/S"]
+        assert sigma_ok(Sg, Sref)
+        assert oracle.reconstruction_error(A, Ug, Sg, Vg) <= float(GOLD[f"rsvd/{name}/{tag}/err"]) + REC_TOL * np.linalg.norm(A)
+        assert tuple(Vg.shape) == tuple(GOLD[f"rsvd/{name}/{tag}/Vshape"])
+
+
+def test_known_answers_on_gpu(engine):
+    for n in (100, 110, 140, 160):
+        A = W.c1_identity(n)
+        U, S, V = engine.rSVD(A, 16, SVDMethod.Jacobi, Omega=W.omega(n, 16))
+        assert np.max(np.abs(S - 1.0)) < 1e-13
+        assert abs(np.linalg.norm(A - (U * S) @ V.T) - np.sqrt(n - 16)) < 1e-11
+    U, S, V = engine.rSVD(W.c1_ramp(100), 16, SVDMethod.Jacobi, Omega=W.omega(100, 16))
+    assert abs(S[0] - 5.77391767e5) / 5.77391767e5 < 1e-8 and abs(S[1] - 1.44312761e3) / 1.44312761e3 < 1e-8 and S[2] < 1e-9
+
+
+@pytest.mark.parametrize("q", [0, 1, 3])
+def test_q_is_a_parameter(engine, oracle, q):
+    rng = np.random.default_rng(q)
+    A = rng.standard_normal((400, 37)) @ rng.standard_normal((37, 150))
+    Om = W.omega(150, 24)
+    Uo, So, Vo = oracle.rsvd(A, Om, 24, q, oracle.JACOBI)
+    Ug, Sg, Vg = engine.rSVD(A, 24, SVDMethod.Jacobi, Omega=Om, q=q)
+    check_rsvd(oracle, A, Ug, Sg, Vg, Uo, So, Vo, 24)
+
+
+def test_device_generated_omega_is_seeded_and_normal(engine):
+    Om1 = engine.generateOmega(4000, 16, seed=5); Om2 = engine.generateOmega(4000, 16, seed=5); Om3 = engine.generateOmega(4000, 16, seed=6)
+    assert np.array_equal(Om1, Om2) and not np.array_equal(Om1, Om3)
+    assert abs(Om1.mean()) < 0.02 and abs(Om1.std() - 1.0) < 0.02
+    A = W.c3_pca(3000, 200)
+    U, S, V = engine.rSVD(A, 20, SVDMethod.Jacobi, Omega=None, q=2, seed=9)       # the reference's calling convention: no Omega
+    Sfull = np.linalg.svd(A, compute_uv=False)[:20]
+    assert np.max(np.abs(S[:10] - Sfull[:10]) / Sfull[:10]) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# configs 2-4 at reduced size against the oracle (full sizes are timed by bench.py / tools)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,gen,l", [
+    ("c2_image_1024", lambda: W.c2_image(1024), 50),
+    ("c3_pca_30000x400", lambda: W.c3_pca(30000, 400), 20),
+    ("c4_pod_20000x600", lambda: W.c4_pod(20000, 600), 64),
+    ("ragged_1001x333_l17", lambda: np.random.default_rng(1).standard_normal((1001, 333)), 17),
+    ("wide_200x900_l40", lambda: np.random.default_rng(2).standard_normal((200, 900)), 40),
+    ("l_equals_n_300x60", lambda: np.random.default_rng(3).standard_normal((300, 60)), 60),
+    ("l128_3000x500", lambda: np.random.default_rng(4).standard_normal((3000, 500)), 128),
+    ("l150_wide_panel_2000x400", lambda: np.random.default_rng(6).standard_normal((2000, 400)), 150),
+])
+def test_configs_vs_oracle(engine, oracle, name, gen, l):
+    A = gen()
+    Om = W.omega(A.shape[1], l)
+    Uo, So, Vo = oracle.rsvd(A, Om, l, 2, oracle.JACOBI)
+    Ug, Sg, Vg = engine.rSVD(A, l, SVDMethod.Jacobi, Omega=Om, q=2)
+    check_rsvd(oracle, A, Ug, Sg, Vg, Uo, So, Vo, l)
+
+
+def test_zero_matrix_and_tiny_inputs(engine):
+    U, S, V = engine.rSVD(np.zeros((50, 30)), 8, SVDMethod.Jacobi, Omega=W.omega(30, 8))
+    assert np.all(S == 0) and np.all(np.isfinite(U)) and np.all(np.isfinite(V))
+    U, S, V = engine.rSVD(np.array([[3.0]]), 1, SVDMethod.Jacobi, Omega=np.array([[1.0]]))
+    assert abs(S[0] - 3.0) < 1e-15 and abs(abs(U[0, 0] * V[0, 0]) - 1.0) < 1e-15
+    A = np.random.default_rng(0).standard_normal((5, 3))
+    U, S, V = engine.rSVD(A, 3, SVDMethod.Jacobi, Omega=W.omega(3, 3))
+    assert np.allclose(S, np.linalg.svd(A, compute_uv=False), rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SVD<method> class, QR, PM, manualMatrixMultiply
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(G.small_inputs().keys()))
+def test_svd_class_vs_oracle_and_golden(engine, oracle, name):
+    B = G.small_inputs()[name]
+    for meth, tag in ((SVDMethod.Jacobi, "jacobi"), (SVDMethod.ParallelJacobi, "pjacobi")):
+        svd = SVD(engine, meth, B); svd.compute()
+        U, S, V = svd.getU(), svd.getS(), svd.getV()
+        Uo, So, Vo, _ = oracle.svd_jacobi(B)
+        assert sigma_ok(S, So) and sigma_ok(S, GOLD[f"svd/{name}/jacobi/S"])
+        assert list(U.shape) + list(V.shape) == list(GOLD[f"svd/{name}/{tag}/shapes"])
+        assert np.linalg.norm(B - (U * S) @ V.T) <= np.linalg.norm(B - (Uo * So) @ Vo.T) + REC_TOL * np.linalg.norm(B)
+        k = min(B.shape)
+        assert np.linalg.norm(U.T @ U - np.eye(k)) <= ORTH_TOL and np.linalg.norm(V.T @ V - np.eye(k)) <= ORTH_TOL
+        assert np.all(np.diff(S) <= 0) and np.all(S >= 0)              # descending, non-negative (SVD_class.hpp:158-178)
+
+
+def test_svd_larger_than_shared_memory(engine):
+    B = np.random.default_rng(8).standard_normal((300, 260))
+    U, S, V = engine.svd(B, SVDMethod.Jacobi)
+    Sref = np.linalg.svd(B, compute_uv=False)
+    assert np.max(np.abs(S - Sref)) <= 1e-12 * Sref[0] and np.linalg.norm(B - (U * S) @ V.T) <= 1e-12 * np.linalg.norm(B)
+
+
+def test_power_backend(engine, oracle):
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((16, 100)) * (0.5 ** np.arange(16))[:, None]
+    U, S, V = engine.svd(B, SVDMethod.Power)
+    Uo, So, Vo, _ = oracle.svd_power(B, 0, seed=1)
+    assert U.shape == Uo.shape == (16, 16) and V.shape == Vo.shape == (100, 100)          # V: n x n with the vectors in ROWS
+    assert np.max(np.abs(S - So) / So) < 1e-8
+    assert np.linalg.norm(B - (U * S) @ V[:16, :]) <= np.linalg.norm(B - (Uo * So) @ Vo[:16, :]) + 1e-8 * np.linalg.norm(B)
+    assert np.array_equal(V[16:, 16:], np.eye(84))                                         # identity-initialised remainder (:83)
+    U2, S2, V2 = engine.svd(B, SVDMethod.Power, r=3)
+    assert np.max(np.abs(S2[:3] - So[:3]) / So[:3]) < 1e-8 and np.all(S2[3:] == 0)
+    # early exit on a rank-2 matrix: conservativeResize to the triplets found (:198-209)
+    R2 = np.outer(rng.standard_normal(12), rng.standard_normal(40)) + np.outer(rng.standard_normal(12), rng.standard_normal(40))
+    U3, S3, V3 = engine.svd(R2, SVDMethod.Power)
+    Uo3, So3, Vo3, info = oracle.svd_power(R2, 0, seed=1)
+    assert S3.shape == So3.shape and U3.shape == Uo3.shape and V3.shape == Vo3.shape
+    # rSVD with the Power back-end: the reference's shapes
+    A = rng.standard_normal((200, 30)) @ np.diag(0.6 ** np.arange(30)) @ rng.standard_normal((30, 80))
+    Ur, Sr, Vr = engine.rSVD(A, 10, SVDMethod.Power, Omega=W.omega(80, 10))
+    assert Ur.shape == (200, 10) and Sr.shape == (10,) and Vr.shape == (80, 80)
+    Sj = engine.rSVD(A, 10, SVDMethod.Jacobi, Omega=W.omega(80, 10))[1]
+    assert np.max(np.abs(Sr - Sj) / Sj[0]) < 1e-6
+
+
+def test_pm(engine, oracle):
+    rng = np.random.default_rng(6)
+    A = rng.standard_normal((60, 25)) @ np.diag(0.7 ** np.arange(25)) @ rng.standard_normal((25, 45))
+    sigma, u, v = engine.PM(A, seed=3)
+    s1 = np.linalg.svd(A, compute_uv=False)[0]
+    assert abs(sigma - s1) / s1 < 1e-9 and abs(np.linalg.norm(u) - 1) < 1e-12 and abs(np.linalg.norm(v) - 1) < 1e-12
+    assert abs(abs(u @ A @ v) - s1) / s1 < 1e-9
+    assert engine.lib.rsvdb_pm_iterations(45) == oracle.pm_iterations(45)
+
+
+@pytest.mark.parametrize("shape", [(4, 3), (100, 16), (777, 33), (5000, 50), (300, 110), (64, 64), (250, 250)])
+def test_qr_reduced_vs_givens_oracle(engine, oracle, shape):
+    rng = np.random.default_rng(shape[0])
+    A = np.arange(1.0, 13.0).reshape(4, 3) if shape == (4, 3) else rng.standard_normal(shape)   # QR_test2.cpp:24-29
+    Q, R = engine.qr_decomposition_reduced(A)
+    n = shape[1]
+    assert np.linalg.norm(Q.T @ Q - np.eye(n)) <= ORTH_TOL and np.linalg.norm(Q @ R - A) <= 1e-12 * np.linalg.norm(A)
+    assert np.all(np.tril(R, -1) == 0) and np.all(np.diag(R) >= 0)
+    if shape[0] * shape[0] <= 1_000_000:                                  # the Givens oracle is O(m^2 n)
+        Qo, Ro = oracle.givens_qr(A, reduced=True)
+        np.testing.assert_allclose(np.abs(R), np.abs(Ro), atol=1e-11 * np.abs(Ro).max())   # python/compare_QR.py:27 (sign-agnostic)
+        full = np.abs(np.diag(Ro)) > 1e-10 * np.abs(Ro).max()             # columns past the numerical rank are an arbitrary completion
+        np.testing.assert_allclose(np.abs(Q[:, full]), np.abs(Qo[:, full]), atol=1e-9)
+
+
+def test_qr_full_and_rank_deficient(engine, oracle):
+    A = np.random.default_rng(1).standard_normal((60, 12))
+    Q, R = engine.qr_decomposition_full(A)
+    assert Q.shape == (60, 60) and R.shape == (60, 12)
+    assert np.linalg.norm(Q.T @ Q - np.eye(60)) <= ORTH_TOL and np.linalg.norm(Q @ R - A) <= 1e-12 * np.linalg.norm(A)
+    B = np.random.default_rng(2).standard_normal((1000, 5)); B = np.hstack([B, B @ np.random.default_rng(3).standard_normal((5, 15))])
+    Q, R = engine.qr_decomposition_reduced(B)                             # rank 5 of 20: Householder still returns an orthonormal Q
+    assert np.linalg.norm(Q.T @ Q - np.eye(20)) <= ORTH_TOL and np.linalg.norm(Q @ R - B) <= 1e-12 * np.linalg.norm(B)
+    with pytest.raises(ValueError):
+        engine.qr_decomposition_reduced(np.ones((3, 5)))
+
+
+def test_manual_matrix_multiply(engine, oracle):
+    rng = np.random.default_rng(7)
+    for (m, k, n) in [(37, 53, 29), (2, 2, 2), (300, 17, 200), (1, 9, 1)]:
+        A = rng.standard_normal((m, k)); B = rng.standard_normal((k, n))
+        np.testing.assert_allclose(engine.manualMatrixMultiply(A, B), oracle.manual_matmul(A, B), rtol=0, atol=1e-13 * k)
+    with pytest.raises(ValueError):                                       # std::invalid_argument, src/matrixOperations.cpp:8-11
+        engine.manualMatrixMultiply(np.ones((3, 4)), np.ones((5, 2)))
+    with pytest.raises(ValueError):                                       # src/rSVD.cpp:122-123
+        engine.rSVD(np.ones((5, 5)), 2, 7)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the GEMM kernels alone (floating-point kernels: torch fp64 reference on the same device data) incl. ragged shapes
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,l,lda", [(128, 16, 8, None), (1000, 300, 20, None), (4096, 4096, 50, None), (5000, 777, 100, 5002),
+                                       (333, 129, 7, 334), (20000, 1000, 104, None), (50000, 2000, 64, None), (130, 50, 128, None),
+                                       (2048, 514, 130, None), (999, 64, 33, 999), (17, 5, 3, 18), (25000, 3000, 100, None)])
+def test_skinny_gemms(engine, m, n, l, lda):
+    import torch
+    dev = torch.device("cuda:0")
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    lda = lda or m
+    A = torch.randn((n, lda), dtype=torch.float64, device=dev); X = torch.randn((l, n), dtype=torch.float64, device=dev)
+    Q = torch.randn((l, m), dtype=torch.float64, device=dev)
+    Y = torch.full((l, m), float("nan"), dtype=torch.float64, device=dev)
+    Z = torch.full((l, n), float("nan"), dtype=torch.float64, device=dev); B = torch.full((n, l), float("nan"), dtype=torch.float64, device=dev)
+    engine.gemm_an_dev(A.data_ptr(), m, n, lda, X.data_ptr(), n, l, Y.data_ptr(), m)
+    engine.gemm_at_dev(A.data_ptr(), m, n, lda, Q.data_ptr(), m, l, Z.data_ptr(), n, False)
+    engine.gemm_at_dev(A.data_ptr(), m, n, lda, Q.data_ptr(), m, l, B.data_ptr(), l, True)
+    Am = A[:, :m].T
+    ref1 = Am @ X.T; ref2 = Am.T @ Q.T
+    tol = 1e-13
+    assert ((Y.T - ref1).norm() / ref1.norm()).item() < tol
+    assert ((Z.T - ref2).norm() / ref2.norm()).item() < tol
+    assert ((B.T - ref2.T).norm() / ref2.norm()).item() < tol
+    # split-K partial sums are reduced in a fixed order: bitwise reproducible
+    Y2 = torch.empty_like(Y); engine.gemm_an_dev(A.data_ptr(), m, n, lda, X.data_ptr(), n, l, Y2.data_ptr(), m)
+    Z2 = torch.empty_like(Z); engine.gemm_at_dev(A.data_ptr(), m, n, lda, Q.data_ptr(), m, l, Z2.data_ptr(), n, False)
+    assert torch.equal(Y, Y2) and torch.equal(Z, Z2)
+    engine.lib.rsvdb_use_own_stream(engine.h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json's headline size (config 5, 200000 x 20000, l = 100, q = 2) through size-independent properties
+# ---------------------------------------------------------------------------------------------------------------------
+def test_full_size_c5_properties(engine):
+    import torch
+    dev = torch.device("cuda:0")
+    m, n, l, q = 200000, 20000, 100, 2
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    A = W.c5_shard_torch(m, n, 0, m, dev)                                  # (n, m) tensor = column-major m x n
+    Om = torch.from_numpy(W.omega(n, l).T.copy()).to(dev)                  # (l, n) tensor = column-major n x l
+    U = torch.empty((l, m), dtype=torch.float64, device=dev); V = torch.empty((l, n), dtype=torch.float64, device=dev)
+    S = torch.empty(l, dtype=torch.float64, device=dev)
+    engine.rsvd_dev(A.data_ptr(), m, n, m, Om.data_ptr(), n, l, q, SVDMethod.Jacobi, U.data_ptr(), m, S.data_ptr(), V.data_ptr(), n)
+    torch.cuda.synchronize()
+    eye = torch.eye(l, dtype=torch.float64, device=dev)
+    assert (U @ U.T - eye).norm().item() <= ORTH_TOL and (V @ V.T - eye).norm().item() <= ORTH_TOL
+    s = S.cpu().numpy()
+    assert np.all(np.diff(s) <= 0) and np.all(s > 0)
+    # singular triplets: A v_i = s_i u_i and A^T u_i = s_i v_i up to the rSVD's own truncation error, which for this
+    # spectrum (10^(-4j/200), noise 1e-6) is far below 1e-6 * s_1 for the leading triplets
+    AV = (V[:10] @ A).T                                                    # m x 10  (A v_i)
+    res = (AV - U[:10].T * S[:10]).norm(dim=0) / S[0]
+    assert res.max().item() < 1e-6
+    AtU = (A @ U[:10].T)                                                   # n x 10  (A^T u_i)
+    res2 = (AtU - V[:10].T * S[:10]).norm(dim=0) / S[0]
+    assert res2.max().item() < 1e-6
+    # the spectrum is known by construction: s_j ~ 10^(-4j/200) up to the O(sqrt(rank/n)) non-orthogonality of the factors
+    expect = 10.0 ** (-4.0 * np.arange(10) / 200)
+    assert np.max(np.abs(s[:10] / expect - 1.0)) < 0.5
+    # linearity: rSVD of 2A has twice the singular values, bit for bit the same vectors up to rounding
+    A.mul_(2.0)
+    S2 = torch.empty_like(S)
+    engine.rsvd_dev(A.data_ptr(), m, n, m, Om.data_ptr(), n, l, q, SVDMethod.Jacobi, U.data_ptr(), m, S2.data_ptr(), V.data_ptr(), n)
+    torch.cuda.synchronize()
+    assert np.max(np.abs(S2.cpu().numpy() / (2.0 * s) - 1.0)) < 1e-10
+    engine.lib.rsvdb_use_own_stream(engine.h)

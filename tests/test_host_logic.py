@@ -1,0 +1,98 @@
+"""CPU tests of the host-side logic: row sharding, deterministic workloads, MatrixMarket IO and -- with two gloo ranks --
+the communication pattern of the row-sharded rSVD (all-gather of TSQR R factors, all-reduce of A^T Q partial sums)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from rsvd_kamaneh_raganato_terrana_b200 import mtx, workloads as W  # noqa: E402
+
+
+def test_row_split_matches_reference_rule():
+    # rows/P (+1 for the first rows%P ranks), reference src/rSVD.cpp:20-23
+    for m, P in [(200000, 8), (10, 3), (7, 7), (5, 8), (100, 1)]:
+        parts = [W.row_split(m, P, r) for r in range(P)]
+        assert parts[0][0] == 0 and sum(rows for _, rows in parts) == m
+        for (o1, r1), (o2, _) in zip(parts, parts[1:]):
+            assert o1 + r1 == o2
+        assert max(r for _, r in parts) - min(r for _, r in parts) <= 1
+
+
+def test_workloads_are_deterministic_and_shaped():
+    assert np.array_equal(W.omega(50, 7), W.omega(50, 7))
+    A = W.c1_ramp(100)
+    assert A[0, 0] == 1.0 and A[99, 99] == 100 * 99 + 100 and np.linalg.matrix_rank(A) == 2
+    assert W.c3_pca(500, 60).shape == (500, 60) and abs(W.c3_pca(500, 60).mean(axis=0)).max() < 1e-12
+    P = W.c4_pod(400, 50)
+    s = np.linalg.svd(P, compute_uv=False)
+    assert s[30] < 1e-8 * s[0]                       # numerically rank-deficient, like real POD snapshots
+    rp, ci, v = W.c4_sparse(1000, 10)
+    assert rp[-1] == len(ci) == len(v) == 11000 and ci.dtype == np.int32 and rp.dtype == np.int64
+
+
+def test_matrix_market_roundtrip(tmp_path):
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((7, 5)); A[A < 0.3] = 0
+    p = tmp_path / "a.mtx"
+    mtx.save_coordinate(p, A, tol=1e-300)
+    assert np.array_equal(mtx.load_dense(p), A)
+    m, n, rowptr, col, val = mtx.load_csr(p)
+    D = np.zeros((m, n))
+    for i in range(m):
+        D[i, col[rowptr[i]:rowptr[i + 1]]] = val[rowptr[i]:rowptr[i + 1]]
+    assert np.array_equal(D, A)
+    q = tmp_path / "s.mtx"
+    mtx.save_array(q, np.arange(4.0))
+    assert np.array_equal(mtx.load_dense(q).ravel(), np.arange(4.0))
+    # the reference's input files are "coordinate real general", 1-based, densified on load (tests/rSVD_test.cpp:54-57)
+    (tmp_path / "i.mtx").write_text("%%MatrixMarket matrix coordinate real general\n3 3 3\n1 1 1.0\n2 2 1.0\n3 3 1.0\n")
+    assert np.array_equal(mtx.load_dense(tmp_path / "i.mtx"), np.eye(3))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _sharded_worker(rank, world, port, m, n, l, q, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle import rsvd_oracle as O
+    import sharded_model
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(99)
+    A = rng.standard_normal((m, 40)) @ np.diag(0.7 ** np.arange(40)) @ rng.standard_normal((40, n))
+    Om = W.omega(n, l)
+    off, rows = W.row_split(m, world, rank)
+    U_p, S, V = sharded_model.rsvd_sharded(A[off:off + rows], Om, l, q, dist, torch, O)
+    np.savez(Path(out_dir) / f"r{rank}.npz", U=U_p, S=S, V=V, off=off)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_rsvd_two_gloo_ranks(tmp_path, oracle):
+    """The multi-GPU path's algorithm (pipeline.cu: qr_inplace sharded branch, gemm_at_phase all-reduce) restated with
+    numpy + gloo on 2 CPU ranks must reproduce the single-rank oracle."""
+    import torch.multiprocessing as mp
+    m, n, l, q, world = 301, 120, 12, 2, 2
+    port = _free_port()
+    mp.spawn(_sharded_worker, args=(world, port, m, n, l, q, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    U = np.vstack([p["U"] for p in parts]); S = parts[0]["S"]; V = parts[0]["V"]
+    assert np.array_equal(parts[0]["S"], parts[1]["S"]) and np.array_equal(parts[0]["V"], parts[1]["V"])   # replicated, bit-identical
+    rng = np.random.default_rng(99)
+    A = rng.standard_normal((m, 40)) @ np.diag(0.7 ** np.arange(40)) @ rng.standard_normal((40, n))
+    Uo, So, Vo = oracle.rsvd(A, W.omega(n, l), l, q, oracle.JACOBI)
+    assert np.all(np.abs(S - So) <= 1e-10 * So[0])
+    assert np.linalg.norm(U.T @ U - np.eye(l)) < 1e-12
+    assert abs(oracle.reconstruction_error(A, U, S, V) - oracle.reconstruction_error(A, Uo, So, Vo)) < 1e-9 * np.linalg.norm(A)
+    assert oracle.subspace_sin_theta(Uo, U) < 1e-8
