@@ -234,6 +234,356 @@ k_house_apply(const double* V, long long ldv, long long rows, int l, const doubl
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Blocked (compact-WY) Householder leaves: panels of 8 reflectors, trailing updates on the FP64 tensor cores.
+//
+// The unblocked leaf above is latency-bound (one block barrier and one shuffle reduction chain per column and per
+// reflector).  Here a panel of 8 columns is factored by ONE warp entirely in registers (no block barrier inside the
+// panel), its 8x8 triangular factor T is formed (Q_p = I - V T V^T, LAPACK dlarft forward/columnwise), and the other
+// columns are updated panel-at-a-time with three small GEMMs per 8-column group, all mma.sync.m8n8k4.f64 (SASS DMMA):
+//   (a) W = V^T C          8 x 8, reduction over the block rows        (the MMA does the cross-lane reduction)
+//   (b) X = op(T) W        8 x 8                                        (op = T^T when factoring, T when forming Q)
+//   (c) C = C - V X        rows x 8
+// Shared-memory layout: column-major with leading dimension BR + 4 (== 4 mod 16) and n-slot permutation
+// PI = {0,1,2,3,5,4,7,6}, which makes every fragment load/store of (a) and (c) bank-conflict free.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int BQ_THREADS = 256;
+constexpr int BQ_WARPS = BQ_THREADS / 32;
+
+__device__ __forceinline__ int perm8(int x) { return (x < 4) ? x : (x ^ 1); }   // {0,1,2,3,5,4,7,6}
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// C-fragment (value of row g, slots 2t / 2t+1 held in c0 / c1) -> B-fragment value M[k][slot g] for this lane.
+__device__ __forceinline__ double frag_c_to_b(double c0, double c1, int k, int g) {
+  const int src = k * 4 + (g >> 1);
+  const double x = __shfl_sync(0xffffffffu, c0, src), y = __shfl_sync(0xffffffffu, c1, src);
+  return (g & 1) ? y : x;
+}
+
+// Apply the block reflector of one panel (clean reflectors Vp: 8 columns, ld LDS, zero above row0; T: 8x8 column-major)
+// to the columns [col_begin, col_end) of S, rows [row0, BR).  transposeT: C <- (I - V T^T V^T) C, else (I - V T V^T) C.
+template <int BR>
+__device__ __forceinline__ void block_reflect(double* S, const double* Vp, const double* Tsm, int row0, int col_begin, int col_end,
+                                              int warp, int nwarps, int lane, bool transposeT) {
+  constexpr int LDS = BR + 4;
+  const int g = lane >> 2, t = lane & 3;
+  for (int n0 = col_begin + 8 * warp; n0 < col_end; n0 += 8 * nwarps) {
+    // (a) W = Vp^T C  (four independent accumulator chains hide the DMMA latency)
+    double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    const int colB = n0 + perm8(g);
+    const bool bval = colB < col_end;
+    const double* cb = S + (size_t)(bval ? colB : col_begin) * LDS + row0 + t;
+    const double* va = Vp + (size_t)g * LDS + row0 + t;
+    const int nk = (BR - row0) >> 2;                                   // k4 steps (even)
+    double av[4], bv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool on = u < nk;
+      av[u] = on ? va[4 * u] : 0.0; bv[u] = (on && bval) ? cb[4 * u] : 0.0;
+    }
+    for (int k = 0; k < nk; k += 4) {
+      double an[4], bn[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                                    // next round's fragments are in flight during the MMAs
+        const bool on = k + 4 + u < nk;
+        an[u] = on ? va[4 * (k + 4 + u)] : 0.0; bn[u] = (on && bval) ? cb[4 * (k + 4 + u)] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dmma884(acc[u], av[u], bv[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { av[u] = an[u]; bv[u] = bn[u]; }
+    }
+    const double w0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);  // W[g][slot 2t]
+    const double w1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);  // W[g][slot 2t+1]
+    // (b) X = op(T) W
+    const double bw0 = frag_c_to_b(w0, w1, t, g), bw1 = frag_c_to_b(w0, w1, t + 4, g);
+    const double t0 = transposeT ? Tsm[t + 8 * g] : Tsm[g + 8 * t];
+    const double t1 = transposeT ? Tsm[(t + 4) + 8 * g] : Tsm[g + 8 * (t + 4)];
+    double x[2] = {0.0, 0.0};
+    dmma884(x, t0, bw0);
+    dmma884(x, t1, bw1);                                               // X[g][slot 2t], X[g][slot 2t+1]
+    // (c) C -= Vp X
+    const double bx0 = -frag_c_to_b(x[0], x[1], t, g), bx1 = -frag_c_to_b(x[0], x[1], t + 4, g);
+    const int col0 = n0 + perm8(2 * t), col1 = n0 + perm8(2 * t + 1);
+    const bool v0 = col0 < col_end, v1 = col1 < col_end;
+    double* p0 = S + (size_t)(v0 ? col0 : col_begin) * LDS + row0 + g;
+    double* p1 = S + (size_t)(v1 ? col1 : col_begin) * LDS + row0 + g;
+    const double* a0p = Vp + (size_t)t * LDS + row0 + g;
+    const double* a1p = Vp + (size_t)(t + 4) * LDS + row0 + g;
+    const int nblk = (BR - row0) >> 3;                                 // 8-row blocks
+    double c[4][2], x0[4], x1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool on = u < nblk; const int r = 8 * u;
+      c[u][0] = (on && v0) ? p0[r] : 0.0; c[u][1] = (on && v1) ? p1[r] : 0.0;
+      x0[u] = on ? a0p[r] : 0.0; x1[u] = on ? a1p[r] : 0.0;
+    }
+    for (int b0 = 0; b0 < nblk; b0 += 4) {
+      double cn[4][2], xn0[4], xn1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                                    // prefetch the next four row blocks
+        const bool on = b0 + 4 + u < nblk; const int r = 8 * (b0 + 4 + u);
+        cn[u][0] = (on && v0) ? p0[r] : 0.0; cn[u][1] = (on && v1) ? p1[r] : 0.0;
+        xn0[u] = on ? a0p[r] : 0.0; xn1[u] = on ? a1p[r] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dmma884(c[u], x0[u], bx0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dmma884(c[u], x1[u], bx1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool on = b0 + u < nblk; const int r = 8 * (b0 + u);
+        if (on && v0) p0[r] = c[u][0];
+        if (on && v1) p1[r] = c[u][1];
+        c[u][0] = cn[u][0]; c[u][1] = cn[u][1]; x0[u] = xn0[u]; x1[u] = xn1[u];
+      }
+    }
+  }
+}
+
+template <int N> __device__ __forceinline__ void warp_sum_n(double (&v)[N]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+}
+
+// All 8 warps factor the panel of pb (<= 8) columns starting at column / diagonal row c0: thread (warp, lane) owns row
+// 32*warp + lane of the panel in registers.  Per reflector there is ONE fused reduction (the column's tail norm and its
+// inner products with the remaining panel columns travel together: warp shuffles, then 8 partials per value through
+// shared memory, double-buffered so that one block barrier per reflector suffices).  The Gram matrix V^T V needed for T
+// (LAPACK dlarft, forward / columnwise) is formed on the tensor cores.
+// Outputs: S panel columns in storage form (R above the diagonal, beta on it, scaled reflectors below), the clean
+// reflectors in Vp (unit diagonal, zeros above, zero columns past pb), T (8x8 column-major, zero-padded), tau.
+// scratch: 2*64 (partials) + 2*8 (diagonal row) + 8*64 (Gram partials) + 64 (Gram) doubles.
+template <int BR>
+__device__ __forceinline__ void panel_factor(double* S, double* Vp, double* Tsm, double* tau_s, double* Tglob, double* scratch,
+                                             int c0, int pb, int warp, int lane) {
+  static_assert(BR == 32 * BQ_WARPS, "one 32-row slab per warp");
+  constexpr int LDS = BR + 4;
+  double* red = scratch;            // [2][8 values][8 warps]
+  double* drow = scratch + 128;     // [2][8]
+  double* Gs = scratch + 144;       // [8 warps][64]
+  double* Gtot = scratch + 656;     // [64]
+  const int i = 32 * warp + lane;
+  double a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = (c < pb) ? S[(size_t)(c0 + c) * LDS + i] : 0.0;
+  double tau[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    tau[r] = 0.0;
+    if (r < pb) {
+      const int d = c0 + r;
+      const int b = r & 1;
+      double p[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) p[c] = (c >= r && i > d) ? a[r] * a[c] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) if (c >= r) p[c] += __shfl_xor_sync(0xffffffffu, p[c], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) if (c >= r) red[b * 64 + c * 8 + warp] = p[c];
+      }
+      if (i == d) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) drow[b * 8 + c] = a[c];
+      }
+      __syncthreads();
+      double tot[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        tot[c] = 0.0;
+        if (c >= r) {
+          const double2* q = reinterpret_cast<const double2*>(red + b * 64 + c * 8);
+          const double2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+          tot[c] = ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
+        }
+      }
+      const double tail = tot[r], x0 = drow[b * 8 + r];
+      double beta, scale;
+      if (tail <= DBL_MIN) { tau[r] = 0.0; beta = x0; scale = 0.0; }
+      else {
+        // beta = -sign(x0) ||x||, tau = (beta - x0)/beta = 1 + |x0|/||x||, scale = 1/(x0 - beta) = sign(x0)/(|x0| + ||x||):
+        // one rsqrt and one reciprocal instead of a square root and two divisions on the reflector's critical path
+        const double n2 = fma(x0, x0, tail);
+        const double inrm = rsqrt(n2);
+        const double nrm = n2 * inrm;
+        const double ax = fabs(x0);
+        beta = (x0 >= 0.0) ? -nrm : nrm;
+        tau[r] = fma(ax, inrm, 1.0);
+        const double rc = __drcp_rn(ax + nrm);
+        scale = (x0 >= 0.0) ? rc : -rc;
+      }
+      const double v = (i > d) ? a[r] * scale : (i == d ? 1.0 : 0.0);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c > r && c < pb) {
+          const double w = tau[r] * fma(scale, tot[c], drow[b * 8 + c]);
+          a[c] = fma(-w, v, a[c]);
+        }
+      }
+      if (i > d) a[r] = v; else if (i == d) a[r] = beta;
+    }
+  }
+  // storage form back to S; clean reflectors to Vp
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (c < pb) S[(size_t)(c0 + c) * LDS + i] = a[c];
+    const int d = c0 + c;
+    Vp[(size_t)c * LDS + i] = (c < pb) ? ((i > d) ? a[c] : (i == d ? 1.0 : 0.0)) : 0.0;
+  }
+  __syncthreads();
+  // Gram partial of this warp's 32 rows on the tensor cores: G = V^T V (A and B fragments are the same values)
+  {
+    const int g = lane >> 2, t = lane & 3;
+    double acc[2] = {0.0, 0.0};
+    if (32 * warp + 31 >= c0) {
+      const double* vg = Vp + (size_t)g * LDS + 32 * warp + t;
+#pragma unroll
+      for (int k0 = 0; k0 < 32; k0 += 4) { const double x = vg[k0]; dmma884(acc, x, x); }
+    }
+    Gs[warp * 64 + g + 8 * (2 * t)] = acc[0];
+    Gs[warp * 64 + g + 8 * (2 * t + 1)] = acc[1];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    double s2 = 0.0;
+#pragma unroll
+    for (int w = 0; w < BQ_WARPS; ++w) s2 += Gs[w * 64 + threadIdx.x];
+    Gtot[threadIdx.x] = s2;
+  }
+  __syncthreads();
+  // T by the dlarft recurrence, one row per thread: T[s][s] = tau_s, T[s][i] = -tau_i * sum_{r=s}^{i-1} T[s][r] G[r][i]
+  if (threadIdx.x < 8) {
+    const int srow = threadIdx.x;
+    double trow[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      double val = 0.0;
+      if (c == srow) val = tau[c];
+      else if (c > srow) {
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < c && r >= srow) acc = fma(trow[r], Gtot[r + 8 * c], acc);
+        val = -tau[c] * acc;
+      }
+      trow[c] = val;
+      Tsm[srow + 8 * c] = val;
+      Tglob[srow + 8 * c] = val;
+    }
+    double tv = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c == srow) tv = tau[c];
+    if (srow < pb) tau_s[c0 + srow] = tv;
+  }
+}
+
+template <int BR>
+__global__ void __launch_bounds__(BQ_THREADS, 1)
+k_house_factor_blk(double* __restrict__ Y, long long ldy, long long rows, int l, double* __restrict__ tau_g,
+                   double* __restrict__ Rstack, long long ldr, double* __restrict__ Tg) {
+  constexpr int LDS = BR + 4;
+  extern __shared__ double sm[];
+  double* S = sm;
+  double* Vp = S + (size_t)l * LDS;
+  double* Tsm = Vp + (size_t)8 * LDS;
+  double* scratch = Tsm + 64;                      // 720 doubles, see panel_factor
+  double* tau_s = scratch + 720;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r0 = (long long)blockIdx.x * BR;
+  const int nrows = (int)min((long long)BR, rows - r0);
+  const int npanels = (l + 7) / 8;
+
+  for (int k = warp; k < l; k += BQ_WARPS) {
+    const double* src = Y + (size_t)k * ldy + r0;
+    for (int i = lane; i < BR; i += 32) S[(size_t)k * LDS + i] = (i < nrows) ? src[i] : 0.0;
+  }
+  __syncthreads();
+  double* Tblock = Tg + (size_t)blockIdx.x * npanels * 64;
+  for (int p = 0; p < npanels; ++p) {
+    const int c0 = 8 * p, pb = min(8, l - c0);
+    panel_factor<BR>(S, Vp, Tsm, tau_s, Tblock + (size_t)p * 64, scratch, c0, pb, warp, lane);
+    __syncthreads();
+    if (c0 + pb < l) block_reflect<BR>(S, Vp, Tsm, c0, c0 + pb, l, warp, BQ_WARPS, lane, true);
+    __syncthreads();
+  }
+  double* Rb = Rstack + (size_t)blockIdx.x * l;
+  for (int k = warp; k < l; k += BQ_WARPS) {
+    double* dst = Y + (size_t)k * ldy + r0;
+    for (int i = lane; i < BR; i += 32) {
+      const double val = S[(size_t)k * LDS + i];
+      if (i < nrows) dst[i] = val;
+      if (i < l) Rb[(size_t)k * ldr + i] = (i <= k) ? val : 0.0;
+    }
+  }
+  for (int j = threadIdx.x; j < l; j += BQ_THREADS) tau_g[(size_t)blockIdx.x * l + j] = tau_s[j];
+}
+
+template <int BR>
+__global__ void __launch_bounds__(BQ_THREADS, 1)
+k_house_apply_blk(const double* V, long long ldv, long long rows, int l, const double* __restrict__ Tg,
+                  const double* __restrict__ Ctop, long long ldc, double* Q, long long ldq) {
+  constexpr int LDS = BR + 4;
+  constexpr int VPT = 8 * BR / BQ_THREADS;       // staged reflector values per thread
+  extern __shared__ double sm[];
+  double* S = sm;
+  double* Vp = S + (size_t)l * LDS;
+  double* Tsm = Vp + (size_t)8 * LDS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r0 = (long long)blockIdx.x * BR;
+  const int nrows = (int)min((long long)BR, rows - r0);
+  const int npanels = (l + 7) / 8;
+
+  for (int k = warp; k < l; k += BQ_WARPS) {
+    for (int i = lane; i < BR; i += 32) {
+      double c = 0.0;
+      if (i < l) c = Ctop ? Ctop[(size_t)k * ldc + (size_t)blockIdx.x * l + i] : (i == k ? 1.0 : 0.0);
+      S[(size_t)k * LDS + i] = c;
+    }
+  }
+  const double* Tblock = Tg + (size_t)blockIdx.x * npanels * 64;
+  // stage panel p: thread e handles elements e, e + 256, ... of the 8 x BR panel (column-major)
+  double vreg[VPT];
+  auto fetch = [&](int p) {
+    const int c0 = 8 * p, pb = min(8, l - c0);
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) {
+      const int e = threadIdx.x + q * BQ_THREADS; const int c = e / BR, i = e % BR;
+      const int d = c0 + c;
+      double v = 0.0;
+      if (c < pb) { if (i > d) v = (i < nrows) ? V[(size_t)d * ldv + r0 + i] : 0.0; else if (i == d) v = 1.0; }
+      vreg[q] = v;
+    }
+  };
+  fetch(npanels - 1);
+  for (int p = npanels - 1; p >= 0; --p) {
+    __syncthreads();                               // previous panel's readers are done with Vp / Tsm
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) {
+      const int e = threadIdx.x + q * BQ_THREADS; const int c = e / BR, i = e % BR;
+      Vp[(size_t)c * LDS + i] = vreg[q];
+    }
+    if (threadIdx.x < 64) Tsm[threadIdx.x] = Tblock[(size_t)p * 64 + threadIdx.x];
+    if (p > 0) fetch(p - 1);
+    __syncthreads();
+    block_reflect<BR>(S, Vp, Tsm, 8 * p, 0, l, warp, BQ_WARPS, lane, false);
+  }
+  __syncthreads();
+  for (int k = warp; k < l; k += BQ_WARPS) {
+    double* dst = Q + (size_t)k * ldq + r0;
+    for (int i = lane; i < nrows; i += 32) dst[i] = S[(size_t)k * LDS + i];
+  }
+}
+
 // Fallback for panels wider than shared memory allows (l > 220 here): one CTA, unblocked Householder directly in global
 // memory (L2-resident for the sizes that reach it).  Same outputs as k_house_factor with a single leaf.
 __global__ void __launch_bounds__(1024, 1)
@@ -330,6 +680,19 @@ int pick_br(int l) {
   return 0;
 }
 
+size_t blk_smem_bytes(int l) { return ((size_t)(l + 8) * (256 + 4) + 64 + 720 + (size_t)l) * sizeof(double); }
+
+cudaError_t set_attr_blk_once() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(k_house_factor_blk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_house_apply_blk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  done = true;
+  return cudaSuccess;
+}
+
 template <int BR> cudaError_t set_attr_once() {
   static bool done = false;
   if (done) return cudaSuccess;
@@ -346,10 +709,12 @@ template <int BR> cudaError_t set_attr_once() {
 cudaError_t Tsqr::plan(long long rows, int l) {
   rows_ = rows; l_ = l; levels_.clear();
   br_ = pick_br(l);
+  blk_ = false;
+  if (l >= 1 && 2 * l <= 256 && blk_smem_bytes(l) <= 227 * 1024) { br_ = 256; blk_ = true; }
   size_t need = 0;
   long long r = rows;
   if (br_ == 0 || r <= 0) {           // single global-memory leaf
-    Level L; L.rows = r; L.nb = 1; L.off_R = need; need += (size_t)l * l; L.off_tau = need; need += (size_t)l;
+    Level L; L.rows = r; L.nb = 1; L.off_R = need; need += (size_t)l * l; L.off_tau = need; need += (size_t)l; L.off_T = need;
     levels_.push_back(L);
     off_top_ = need; need += (size_t)l * l;
     off_scratch_ = need; need += (size_t)std::max<long long>(r, 1) * l;   // apply_global cannot run in place
@@ -358,6 +723,7 @@ cudaError_t Tsqr::plan(long long rows, int l) {
       Level L; L.rows = r; L.nb = (int)((r + br_ - 1) / br_);
       L.off_R = need; need += (size_t)L.nb * l * l;
       L.off_tau = need; need += (size_t)L.nb * l;
+      L.off_T = need; if (blk_) need += (size_t)L.nb * ((l + 7) / 8) * 64;
       levels_.push_back(L);
       if (L.nb == 1) break;
       r = (long long)L.nb * l;
@@ -382,6 +748,10 @@ cudaError_t Tsqr::factor(cudaStream_t st, double* Y, long long ldy, int* launche
     const long long ldr = (long long)L.nb * l_;
     const size_t smem = ((size_t)br_ * l_ + l_) * sizeof(double);
     cudaError_t e;
+    if (blk_) {
+      e = set_attr_blk_once(); if (e != cudaSuccess) return e;
+      k_house_factor_blk<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
+    } else
     switch (br_) {
       case 512: e = set_attr_once<512>(); if (e != cudaSuccess) return e;
         k_house_factor<512><<<L.nb, QR_THREADS, smem, st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr); break;
@@ -422,6 +792,9 @@ cudaError_t Tsqr::form_q(cudaStream_t st, double* Y, long long ldy, const double
     const double* C; long long ldcc;
     if (i == (int)levels_.size() - 1) { C = Ctop; ldcc = ldc; } else { C = base + L.off_R; ldcc = (long long)L.nb * l_; }
     const size_t smem = ((size_t)br_ * l_ + l_) * sizeof(double);
+    if (blk_) {
+      k_house_apply_blk<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(V, ldv, L.rows, l_, base + L.off_T, C, ldcc, V, ldv);
+    } else
     switch (br_) {
       case 512: k_house_apply<512><<<L.nb, QR_THREADS, smem, st>>>(V, ldv, L.rows, l_, base + L.off_tau, C, ldcc, V, ldv); break;
       case 256: k_house_apply<256><<<L.nb, QR_THREADS, smem, st>>>(V, ldv, L.rows, l_, base + L.off_tau, C, ldcc, V, ldv); break;

@@ -22,11 +22,12 @@ class Tsqr {
   int depth() const { return (int)levels_.size(); }
 
  private:
-  struct Level { long long rows; int nb; size_t off_R; size_t off_tau; };
+  struct Level { long long rows; int nb; size_t off_R; size_t off_tau; size_t off_T; };
   GemmWorkspace* ws_;
   std::vector<Level> levels_;
   long long rows_ = 0;
   int l_ = 0, br_ = 0;
+  bool blk_ = false;                   // blocked (compact-WY, DMMA) leaves
   size_t off_top_ = 0, off_scratch_ = 0;
 };
 

@@ -290,3 +290,41 @@ def test_full_size_c5_properties(engine):
     torch.cuda.synchronize()
     assert np.max(np.abs(S2.cpu().numpy() / (2.0 * s) - 1.0)) < 1e-10
     engine.lib.rsvdb_use_own_stream(engine.h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the C++ drop-in headers (include/rSVD.hpp, SVD_class.hpp, QR.hpp, PM.hpp, matrixOperations.hpp): a C++ caller written
+# against the reference's own API, linked to librsvdb.so
+# ---------------------------------------------------------------------------------------------------------------------
+def test_cpp_dropin_headers(oracle, tmp_path):
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "rsvd_dropin_test"
+    libdir = root / "rsvd_kamaneh_raganato_terrana_b200"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-I", str(root / "include"), "-o", str(exe), str(root / "tests" / "cpp" / "rsvd_dropin_test.cpp"),
+                    "-L", str(libdir), "-lrsvdb", f"-Wl,-rpath,{libdir}"], check=True)
+    m, n, l = 300, 120, 20
+    rng = np.random.default_rng(77)
+    A = np.asfortranarray(rng.standard_normal((m, 50)) @ np.diag(0.8 ** np.arange(50)) @ rng.standard_normal((50, n)))
+    A.ravel(order="F").tofile(tmp_path / "A.bin")
+    out = subprocess.run([str(exe), str(tmp_path / "A.bin"), str(m), str(n), str(l), str(tmp_path / "o")], check=True, capture_output=True, text=True).stdout
+    rd = lambda name, shape: np.fromfile(tmp_path / f"o_{name}.bin").reshape(shape, order="F")
+    Om = rd("Omega", (n, l)); U = rd("U", (m, l)); S = rd("S", (l,)); V = rd("V", (n, l)); Q = rd("Q", (m, l))
+    assert "rSVD: U 300 x 20, S 20, V 120 x 20" in out and "SVD<Jacobi>: U 300 x 120, V 120 x 120" in out
+    assert "invalid_argument paths: 3" in out                                    # both reference throw sites are kept
+    Uo, So, Vo = oracle.rsvd(A, Om, l, 2, oracle.JACOBI)
+    check_rsvd(oracle, A, U, S, V, Uo, So, Vo, l)
+    assert oracle.subspace_sin_theta(oracle.intermediate_step(A, Om, l, 2), Q) < SIN_TOL
+    Sfull = np.linalg.svd(A, compute_uv=False)
+    assert np.max(np.abs(rd("Sfull", (n,)) - Sfull)) <= 1e-12 * Sfull[0]
+    assert np.max(np.abs(rd("S2", (l,))[:8] - Sfull[:8]) / Sfull[:8]) < 1e-6     # 6-argument call: internal Omega, q = 2
+    Qr, Rr = rd("QRq", (m, n)), rd("QRr", (n, n))
+    assert np.linalg.norm(Qr @ Rr - A) <= 1e-12 * np.linalg.norm(A) and np.all(np.diag(Rr) >= 0)
+    assert "QR class vs free function |dR|_1 = 0" in out
+    assert abs(rd("pm", (1,))[0] - Sfull[0]) / Sfull[0] < 1e-9
+    np.testing.assert_allclose(rd("AOmega", (m, l)), A @ Om, rtol=0, atol=1e-12 * np.linalg.norm(A @ Om))
+    ok, c, s = True, *[float(x.split("=")[1]) for x in out.split("makeJacobi ")[1].split()[1:3]]
+    lib = oracle._lib(); import ctypes
+    cc = ctypes.c_double(); ss = ctypes.c_double()
+    lib.oc_make_jacobi(ctypes.c_double(2.0), ctypes.c_double(0.5), ctypes.c_double(1.0), ctypes.byref(cc), ctypes.byref(ss))
+    assert (c, s) == (cc.value, ss.value)                                         # JacobiRotation::makeJacobi is bit-identical

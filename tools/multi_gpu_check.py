@@ -1,0 +1,48 @@
+"""Multi-GPU parity: run under torchrun with N ranks; every rank holds a row shard; compare with the single-process oracle."""
+import json, os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, ".")
+from rsvd_kamaneh_raganato_terrana_b200 import Engine, SVDMethod, workloads as W
+from oracle import rsvd_oracle as O
+
+world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+torch.cuda.set_device(local); dev = torch.device(f"cuda:{local}")
+E = Engine(local)
+uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+if rank == 0:
+    uid = torch.frombuffer(bytearray(E.comm_unique_id()), dtype=torch.uint8).to(dev)
+dist.broadcast(uid, 0)
+E.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+E.set_stream(torch.cuda.current_stream().cuda_stream)
+ok_all = True
+for (m, n, l, q, gen) in [(3001, 400, 32, 2, "pod"), (20000, 1500, 100, 2, "gauss"), (1000, 300, 16, 1, "rank2"), (50000, 2000, 64, 2, "pod")]:
+    rng = np.random.default_rng(42)
+    if gen == "pod": A = W.c4_pod(m, n)
+    elif gen == "rank2": A = np.asfortranarray(np.outer(rng.standard_normal(m), rng.standard_normal(n)) + np.outer(rng.standard_normal(m), rng.standard_normal(n)))
+    else: A = np.asfortranarray(rng.standard_normal((m, 60)) @ np.diag(0.9 ** np.arange(60)) @ rng.standard_normal((60, n)) + 1e-3 * rng.standard_normal((m, n)))
+    Om = W.omega(n, l)
+    off, rows = W.row_split(m, world, rank)
+    # host API on the local shard (every rank calls collectively)
+    U_p, S, V = E.rSVD(A[off:off + rows], l, SVDMethod.Jacobi, Omega=Om, q=q)
+    Ut = torch.from_numpy(np.ascontiguousarray(U_p)).to(dev)
+    parts = [torch.empty((W.row_split(m, world, r)[1], U_p.shape[1]), dtype=torch.float64, device=dev) for r in range(world)]
+    dist.all_gather(parts, Ut)
+    U = torch.cat(parts, 0).cpu().numpy()
+    Sall = [torch.empty(len(S), dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(Sall, torch.from_numpy(S).to(dev))
+    same_S = all(torch.equal(Sall[0], s) for s in Sall)
+    if rank == 0:
+        Uo, So, Vo = O.rsvd(A, Om, l, q, O.JACOBI)
+        okS, relS = O.sigma_close(S, So)
+        eg, eo = O.reconstruction_error(A, U, S, V), O.reconstruction_error(A, Uo, So, Vo)
+        orthU = np.linalg.norm(U.T @ U - np.eye(U.shape[1]))
+        ok = okS and eg <= eo + 1e-8 * np.linalg.norm(A) and orthU < 1e-10 and same_S
+        ok_all &= ok
+        print(json.dumps({"multi_gpu": [m, n, l, q, gen], "world": world, "ok": bool(ok), "relS": relS, "err_gpu": eg, "err_oracle": eo, "orthU": orthU, "S_identical_on_all_ranks": same_S}), flush=True)
+if rank == 0:
+    print(json.dumps({"all_ok": bool(ok_all)}), flush=True)
+E.close()
+dist.destroy_process_group()
