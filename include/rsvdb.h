@@ -131,6 +131,19 @@ RSVDB_API int rsvdb_pm_host(rsvdb_ctx* ctx, const double* A, int64_t m, int64_t 
  * Returns RSVDB_ERR_INVALID_ARGUMENT when ka != kb (the reference throws std::invalid_argument, :8-11). */
 RSVDB_API int rsvdb_gemm_host(rsvdb_ctx* ctx, const double* A, int64_t m, int64_t ka, int64_t lda, const double* B, int64_t kb,
                               int64_t n, int64_t ldb, double* C, int64_t ldc);
+/* ---- sparse inputs (CSR; int64 row pointers, int32 column indices, 0-based) ----------------------------------------
+ * The reference densifies every MatrixMarket input before rSVD (tests/rSVD_test.cpp:54-57); these entry points run
+ * the same algorithm (src/rSVD.cpp:57-133) on the CSR directly.  A is this rank's row block. */
+RSVDB_API int rsvdb_rsvd_csr_host(rsvdb_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
+                                  const double* values, const double* Omega, int64_t ldo, uint64_t seed, int l, int q, int method,
+                                  double* U, int64_t ldu, double* S, double* V, int64_t ldv);
+RSVDB_API int rsvdb_rsvd_csr_dev(rsvdb_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* d_rowptr, const int32_t* d_colidx,
+                                 const double* d_values, const double* dOmega, int64_t ldo, uint64_t seed, int l, int q, int method,
+                                 double* dU, int64_t ldu, double* dS, double* dV, int64_t ldv);
+/* Y (m x l, ROW-major) = A (CSR) * X (n x l, ROW-major): the SpMM building block (HBM-bound; see csrc/spmm.cu). */
+RSVDB_API int rsvdb_csr_spmm_dev(rsvdb_ctx* ctx, int64_t m, const int64_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                 const double* dX_rowmajor, int l, double* dY_rowmajor);
+
 /* Number of power iterations PM runs for an n-column matrix (src/PM.cpp:25-28). */
 RSVDB_API int rsvdb_pm_iterations(int64_t ncols);
 

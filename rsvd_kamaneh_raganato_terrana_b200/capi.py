@@ -76,6 +76,9 @@ def _declare(lib):
         "rsvdb_qr_host": [vp, vp, i64, i64, i64, c_int, vp, i64, vp, i64],
         "rsvdb_pm_host": [vp, vp, i64, i64, i64, u64, POINTER(c_double), vp, vp],
         "rsvdb_gemm_host": [vp, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64],
+        "rsvdb_rsvd_csr_host": [vp, i64, i64, i64, vp, vp, vp, vp, i64, u64, c_int, c_int, c_int, vp, i64, vp, vp, i64],
+        "rsvdb_rsvd_csr_dev": [vp, i64, i64, i64, vp, vp, vp, vp, i64, u64, c_int, c_int, c_int, vp, i64, vp, vp, i64],
+        "rsvdb_csr_spmm_dev": [vp, i64, vp, vp, vp, vp, c_int, vp],
     }
     for name, argtypes in sig.items():
         getattr(lib, name).argtypes = argtypes

@@ -7,6 +7,7 @@
 #include "comm.cuh"
 #include "context.cuh"
 #include "pipeline.cuh"
+#include "spmm.cuh"
 #include "tsqr.cuh"
 
 using namespace rsvdb;
@@ -384,6 +385,54 @@ int rsvdb_pm_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t l
   RSVDB_TRY(d2h(c, u, m, du, ldA, m, 1));
   RSVDB_TRY(d2h(c, v, n, dv, ldN, n, 1));
   RSVDB_TRY(d2h(c, sigma, 1, dS, 1, 1, 1));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_csr_spmm_dev(rsvdb_ctx* c, int64_t m, const int64_t* rp, const int32_t* ci, const double* v, const double* X, int l, double* Y) {
+  if (!c || m < 0 || l <= 0) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "csr_spmm: bad shape");
+  return csr_spmm_rm(c, m, rp, ci, v, X, l, Y);
+}
+
+int rsvdb_rsvd_csr_dev(rsvdb_ctx* c, int64_t m, int64_t n, int64_t nnz, const int64_t* rp, const int32_t* ci, const double* v,
+                       const double* dOmega, int64_t ldo, uint64_t seed, int l, int q, int method, double* dU, int64_t ldu, double* dS,
+                       double* dV, int64_t ldv) {
+  if (!c || m < 0 || n <= 0 || nnz < 0 || ldo < n || ldu < m || ldv < n) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "rsvd_csr: bad shape");
+  return rsvd_csr_device(c, m, n, nnz, rp, ci, v, dOmega, ldo, l, q, method, dU, ldu, dS, dV, ldv, seed);
+}
+
+int rsvdb_rsvd_csr_host(rsvdb_ctx* c, int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx, const double* values,
+                        const double* Omega, int64_t ldo, uint64_t seed, int l, int q, int method, double* U, int64_t ldu, double* S,
+                        double* V, int64_t ldv) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (method != 0 && method != 1 && method != 2) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "Unsupported SVD method");
+  if (!rowptr || (nnz > 0 && (!colidx || !values)) || !U || !S || !V || m < 0 || n <= 0 || nnz < 0 || l <= 0 || q < 0 || (Omega && ldo < n) ||
+      ldu < m || ldv < n)
+    return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "rSVD (CSR): bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t k = std::min<int64_t>(l, n);
+  const int64_t ldA = even_ld(m), ldO = even_ld(n);
+  const size_t need = (IoArena::pad((size_t)m + 2) + IoArena::pad((size_t)nnz / 2 + 2) + IoArena::pad((size_t)nnz + 2) + IoArena::pad((size_t)ldO * l) +
+                       IoArena::pad((size_t)ldA * l) + IoArena::pad((size_t)ldO * l) + IoArena::pad((size_t)l)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  int64_t* drp = reinterpret_cast<int64_t*>(ar.take((size_t)m + 2)); int32_t* dci = reinterpret_cast<int32_t*>(ar.take((size_t)nnz / 2 + 2));
+  double* dv = ar.take((size_t)nnz + 2); double* dO = ar.take((size_t)ldO * l); double* dU = ar.take((size_t)ldA * l);
+  double* dV = ar.take((size_t)ldO * l); double* dS = ar.take((size_t)l);
+  {
+    PhaseTimer pt(c, PH_COPY);
+    RSVDB_CUDA(c, cudaMemcpyAsync(drp, rowptr, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (nnz > 0) {
+      RSVDB_CUDA(c, cudaMemcpyAsync(dci, colidx, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+      RSVDB_CUDA(c, cudaMemcpyAsync(dv, values, (size_t)nnz * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+  }
+  if (Omega) { RSVDB_TRY(h2d(c, dO, ldO, Omega, ldo, n, l)); }
+  else { RSVDB_TRY(rsvdb_generate_omega_dev(c, n, l, seed, dO, ldO)); }
+  RSVDB_TRY(rsvd_csr_device(c, m, n, nnz, drp, dci, dv, dO, ldO, l, q, method, dU, ldA, dS, dV, ldO, seed));
+  RSVDB_TRY(d2h(c, U, ldu, dU, ldA, m, k));
+  RSVDB_TRY(d2h(c, S, k, dS, k, k, 1));
+  RSVDB_TRY(d2h(c, V, ldv, dV, ldO, n, k));
   RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RSVDB_OK;
 }

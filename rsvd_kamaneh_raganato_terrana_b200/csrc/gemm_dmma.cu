@@ -367,14 +367,20 @@ bool make_map(CUtensorMap* map, const double* base, long long rows, long long co
 
 bool tma_addressable(const double* p, long long ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 1) == 0; }
 
-void choose_split(int ntiles, int ksteps, int nsm, int* nsplit, int* kchunk) {
-  int best = 1; double best_eff = 0.0;
-  const int smax = std::max(1, std::min(64, ksteps / 8));
+// Cut the reduction into nsplit slabs so that (tiles x splits) fills the SMs in whole waves.  Cost model in units of one
+// k-step of one CTA: waves(S) * ceil(ksteps / S) + (S > 1 ? (S + 1) * reduce_units : 0), where reduce_units is the time
+// to stream one partial output through HBM (the fixed-order reduction reads S partials and writes one result).
+void choose_split(int ntiles, int ksteps, int nsm, long long out_elems, int nb, int* nsplit, int* kchunk) {
+  const double kstep_us = (double)BM * (8.0 * nb) * BK * 2.0 / (37.1e12 / nsm) * 1e6;   // one CTA, one slab, at the DMMA rate
+  const double reduce_units = ((double)out_elems * 8.0 / 6.5e12 * 1e6) / kstep_us;
+  int best = 1; double best_t = 1e300;
+  const int smax = std::max(1, std::min(48, ksteps / 8));
   for (int s = 1; s <= smax; ++s) {
     const long long units = (long long)ntiles * s;
-    const double eff = (double)units / (double)(((units + nsm - 1) / nsm) * nsm);
-    if (eff > best_eff + 0.03) { best_eff = eff; best = s; }
-    if (best_eff >= 0.94) break;
+    const long long waves = (units + nsm - 1) / nsm;
+    const int per = (ksteps + s - 1) / s;
+    double t = (double)waves * per + (s > 1 ? (s + 1) * reduce_units + 4.0 : 0.0);
+    if (t < best_t * 0.995) { best_t = t; best = s; }
   }
   const int per = (ksteps + best - 1) / best;
   *kchunk = per * BK;
@@ -434,7 +440,7 @@ cudaError_t gemm_an(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
   CUtensorMap tA;
   if (!make_map(&tA, A, M, K, lda, BK)) return cudaErrorInvalidValue;
   const int ntiles = (int)((M + BM - 1) / BM), ksteps = (int)((K + BK - 1) / BK);
-  int nsplit, kchunk; choose_split(ntiles, ksteps, nsm, &nsplit, &kchunk);
+  int nsplit, kchunk; choose_split(ntiles, ksteps, nsm, M * std::min(N, 128), (std::min(N, 128) + 7) / 8, &nsplit, &kchunk);
   for (int n0 = 0; n0 < N; n0 += 128) {
     const int nc = std::min(128, N - n0), NB = (nc + 7) / 8;
     CUtensorMap tX;
@@ -491,7 +497,7 @@ cudaError_t gemm_at(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
   CUtensorMap tA;
   if (!make_map(&tA, A, K, M, lda, BM)) return cudaErrorInvalidValue;
   const int ntiles = (int)((M + BM - 1) / BM), ksteps = (int)((K + BK - 1) / BK);
-  int nsplit, kchunk; choose_split(ntiles, ksteps, nsm, &nsplit, &kchunk);
+  int nsplit, kchunk; choose_split(ntiles, ksteps, nsm, M * std::min(N, 128), (std::min(N, 128) + 7) / 8, &nsplit, &kchunk);
   for (int n0 = 0; n0 < N; n0 += 128) {
     const int nc = std::min(128, N - n0), NB = (nc + 7) / 8;
     CUtensorMap tQ;

@@ -166,6 +166,24 @@ class Engine:
             return U, S, _power_v_layout(V, n, k, k)
         return U, S, V
 
+    def rSVD_csr(self, rowptr, colidx, values, shape, l: int, method=SVDMethod.Jacobi, Omega=None, q: int = 2, seed: int = 0):
+        """rSVD of a CSR matrix (int64 row pointers, int32 column indices) without densifying it -- the reference
+        densifies every .mtx first (tests/rSVD_test.cpp:54-57).  Same outputs as rSVD()."""
+        m, n = shape
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int64); colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        nnz = int(rowptr[-1])
+        k = min(l, n)
+        U = np.zeros((m, max(k, 1)), order="F"); S = np.zeros(max(k, 1)); V = np.zeros((n, max(k, 1)), order="F")
+        om_ptr, ldo = None, 0
+        if Omega is not None:
+            Omega = _f(Omega); om_ptr, ldo = _ptr(Omega), n
+        self._check(self.lib.rsvdb_rsvd_csr_host(self.h, m, n, nnz, rowptr.ctypes.data, colidx.ctypes.data, values.ctypes.data, om_ptr, ldo,
+                                                 seed, l, q, int(method), _ptr(U), max(m, 1), _ptr(S), _ptr(V), n))
+        if int(method) == SVDMethod.Power:
+            return U, S, _power_v_layout(V, n, k, k)
+        return U, S, V
+
     def qr_decomposition_reduced(self, A):
         """src/QR.cpp:43-80: Q m x n, R n x n."""
         A = _f(A); m, n = A.shape

@@ -328,3 +328,83 @@ def test_cpp_dropin_headers(oracle, tmp_path):
     cc = ctypes.c_double(); ss = ctypes.c_double()
     lib.oc_make_jacobi(ctypes.c_double(2.0), ctypes.c_double(0.5), ctypes.c_double(1.0), ctypes.byref(cc), ctypes.byref(ss))
     assert (c, s) == (cc.value, ss.value)                                         # JacobiRotation::makeJacobi is bit-identical
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K7: sparse inputs (CSR) -- the reference densifies every .mtx (tests/rSVD_test.cpp:54-57); the oracle does the same
+# ---------------------------------------------------------------------------------------------------------------------
+def _random_csr(m, n, per_row, seed):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    rows = np.repeat(np.arange(m), per_row); cols = rng.integers(0, n, size=m * per_row); vals = rng.standard_normal(m * per_row)
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(m, n)); A.sum_duplicates(); A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("m,n,l", [(1000, 700, 16), (5000, 3000, 64), (333, 1001, 7), (2000, 2000, 100)])
+def test_csr_spmm_building_block(engine, m, n, l):
+    import torch
+    A = _random_csr(m, n, 9, m + n)
+    dev = torch.device("cuda:0"); engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    X = np.random.default_rng(1).standard_normal((n, l))
+    rp = torch.from_numpy(A.indptr.astype(np.int64)).to(dev); ci = torch.from_numpy(A.indices.astype(np.int32)).to(dev)
+    va = torch.from_numpy(A.data).to(dev); Xd = torch.from_numpy(np.ascontiguousarray(X)).to(dev)
+    Yd = torch.full((m, l), float("nan"), dtype=torch.float64, device=dev)
+    rc = engine.lib.rsvdb_csr_spmm_dev(engine.h, m, rp.data_ptr(), ci.data_ptr(), va.data_ptr(), Xd.data_ptr(), l, Yd.data_ptr())
+    assert rc == 0
+    ref = A @ X
+    assert np.linalg.norm(Yd.cpu().numpy() - ref) <= 1e-13 * np.linalg.norm(ref)
+    engine.lib.rsvdb_use_own_stream(engine.h)
+
+
+@pytest.mark.parametrize("name", ["sparse_matrix", "sparse_matrix100", "sparse_matrix160"])
+def test_rsvd_csr_on_reference_inputs(engine, oracle, name, tmp_path):
+    """The reference's own input files (regenerated from their definition), read as MatrixMarket -> CSR, never densified
+    on the GPU side; the oracle densifies like the reference."""
+    from rsvd_kamaneh_raganato_terrana_b200 import mtx
+    A = dict(W.C1_CASES)[name]()
+    p = tmp_path / f"{name}.mtx"
+    mtx.save_coordinate(p, A, tol=0.0 if name == "sparse_matrix" else 1e-300)
+    m, n, rowptr, col, val = mtx.load_csr(p)
+    assert np.array_equal(mtx.load_dense(p), A)
+    Om = W.omega(n, W.C1_L)
+    Ug, Sg, Vg = engine.rSVD_csr(rowptr, col, val, (m, n), W.C1_L, SVDMethod.Jacobi, Omega=Om, q=2)
+    Uo, So, Vo = oracle.rsvd(A, Om, W.C1_L, 2, oracle.JACOBI)
+    check_rsvd(oracle, A, Ug, Sg, Vg, Uo, So, Vo, W.C1_L)
+    assert sigma_ok(Sg, GOLD[f"rsvd/{name}/jacobi/S"])
+
+
+def test_rsvd_csr_vs_dense_oracle(engine, oracle):
+    A = _random_csr(6000, 2500, 10, 3)
+    Ad = np.asfortranarray(A.toarray())
+    l = 48; Om = W.omega(2500, l)
+    Ug, Sg, Vg = engine.rSVD_csr(A.indptr, A.indices, A.data, A.shape, l, SVDMethod.Jacobi, Omega=Om, q=2)
+    Uo, So, Vo = oracle.rsvd(Ad, Om, l, 2, oracle.JACOBI)
+    check_rsvd(oracle, Ad, Ug, Sg, Vg, Uo, So, Vo, l)
+    Ud, Sd, Vd = engine.rSVD(Ad, l, SVDMethod.Jacobi, Omega=Om, q=2)            # sparse and dense CUDA paths agree
+    assert sigma_ok(Sg, Sd)
+    # empty rows / columns and an empty matrix
+    import scipy.sparse as sp
+    B = sp.csr_matrix((np.array([2.0, -3.0]), (np.array([0, 4]), np.array([1, 6]))), shape=(7, 9))
+    U, S, V = engine.rSVD_csr(B.indptr, B.indices, B.data, B.shape, 3, SVDMethod.Jacobi, Omega=W.omega(9, 3))
+    assert np.allclose(S, [3.0, 2.0, 0.0], atol=1e-13)
+    Z = sp.csr_matrix((5, 4))
+    U, S, V = engine.rSVD_csr(Z.indptr, Z.indices, Z.data, Z.shape, 2, SVDMethod.Jacobi, Omega=W.omega(4, 2))
+    assert np.all(S == 0) and np.all(np.isfinite(U)) and np.all(np.isfinite(V))
+
+
+def test_rsvd_csr_full_size_properties(engine):
+    """BASELINE.json config 4, sparse variant: 1M x 1M CSR, ~11 nnz/row, l = 64, q = 2 -- size-independent properties."""
+    import scipy.sparse as sp
+    m = 1_000_000; l = 64
+    rowptr, col, val = W.c4_sparse(m, 10)
+    U, S, V = engine.rSVD_csr(rowptr, col, val, (m, m), l, SVDMethod.Jacobi, Omega=None, q=2, seed=11)
+    assert np.linalg.norm(U.T @ U - np.eye(l)) <= ORTH_TOL and np.linalg.norm(V.T @ V - np.eye(l)) <= ORTH_TOL
+    assert np.all(np.diff(S) <= 0) and S[-1] > 0
+    A = sp.csr_matrix((val, col, rowptr), shape=(m, m))
+    # U = Q Utilde with B = Q^T A = Utilde S V^T  =>  A^T u_i = s_i v_i exactly (up to rounding), for every i
+    res = np.linalg.norm(A.T @ U - V * S, axis=0) / S[0]
+    assert res.max() < 1e-12
+    # s_i = ||Q^T A v_i|| <= ||A v_i||  (Q has orthonormal columns): every computed value is a lower bound
+    AV = A @ V[:, :8]
+    assert np.all(np.linalg.norm(AV, axis=0) >= S[:8] * (1 - 1e-12))
