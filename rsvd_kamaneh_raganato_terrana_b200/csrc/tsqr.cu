@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 namespace rsvdb {
 
@@ -247,8 +248,9 @@ k_house_apply(const double* V, long long ldv, long long rows, int l, const doubl
 // Shared-memory layout: column-major with leading dimension BR + 4 (== 4 mod 16) and n-slot permutation
 // PI = {0,1,2,3,5,4,7,6}, which makes every fragment load/store of (a) and (c) bank-conflict free.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int BQ_THREADS = 256;
+constexpr int BQ_THREADS = 512;
 constexpr int BQ_WARPS = BQ_THREADS / 32;
+constexpr int BQ_ROW_WARPS = 8;                 // warps that own a 32-row slab of the panel (BR = 256)
 
 __device__ __forceinline__ int perm8(int x) { return (x < 4) ? x : (x ^ 1); }   // {0,1,2,3,5,4,7,6}
 
@@ -279,23 +281,16 @@ __device__ __forceinline__ void block_reflect(double* S, const double* Vp, const
     const double* cb = S + (size_t)(bval ? colB : col_begin) * LDS + row0 + t;
     const double* va = Vp + (size_t)g * LDS + row0 + t;
     const int nk = (BR - row0) >> 2;                                   // k4 steps (even)
-    double av[4], bv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool on = u < nk;
-      av[u] = on ? va[4 * u] : 0.0; bv[u] = (on && bval) ? cb[4 * u] : 0.0;
-    }
     for (int k = 0; k < nk; k += 4) {
-      double an[4], bn[4];
+      double av[4], bv[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {                                    // next round's fragments are in flight during the MMAs
-        const bool on = k + 4 + u < nk;
-        an[u] = on ? va[4 * (k + 4 + u)] : 0.0; bn[u] = (on && bval) ? cb[4 * (k + 4 + u)] : 0.0;
+      for (int u = 0; u < 4; ++u) {
+        const bool on = k + u < nk;
+        av[u] = on ? va[4 * (k + u)] : 0.0;
+        bv[u] = (on && bval) ? cb[4 * (k + u)] : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) dmma884(acc[u], av[u], bv[u]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { av[u] = an[u]; bv[u] = bn[u]; }
     }
     const double w0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);  // W[g][slot 2t]
     const double w1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);  // W[g][slot 2t+1]
@@ -315,20 +310,13 @@ __device__ __forceinline__ void block_reflect(double* S, const double* Vp, const
     const double* a0p = Vp + (size_t)t * LDS + row0 + g;
     const double* a1p = Vp + (size_t)(t + 4) * LDS + row0 + g;
     const int nblk = (BR - row0) >> 3;                                 // 8-row blocks
-    double c[4][2], x0[4], x1[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool on = u < nblk; const int r = 8 * u;
-      c[u][0] = (on && v0) ? p0[r] : 0.0; c[u][1] = (on && v1) ? p1[r] : 0.0;
-      x0[u] = on ? a0p[r] : 0.0; x1[u] = on ? a1p[r] : 0.0;
-    }
     for (int b0 = 0; b0 < nblk; b0 += 4) {
-      double cn[4][2], xn0[4], xn1[4];
+      double c[4][2], x0[4], x1[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {                                    // prefetch the next four row blocks
-        const bool on = b0 + 4 + u < nblk; const int r = 8 * (b0 + 4 + u);
-        cn[u][0] = (on && v0) ? p0[r] : 0.0; cn[u][1] = (on && v1) ? p1[r] : 0.0;
-        xn0[u] = on ? a0p[r] : 0.0; xn1[u] = on ? a1p[r] : 0.0;
+      for (int u = 0; u < 4; ++u) {
+        const bool on = b0 + u < nblk; const int r = 8 * (b0 + u);
+        c[u][0] = (on && v0) ? p0[r] : 0.0; c[u][1] = (on && v1) ? p1[r] : 0.0;
+        x0[u] = on ? a0p[r] : 0.0; x1[u] = on ? a1p[r] : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) dmma884(c[u], x0[u], bx0);
@@ -339,7 +327,6 @@ __device__ __forceinline__ void block_reflect(double* S, const double* Vp, const
         const bool on = b0 + u < nblk; const int r = 8 * (b0 + u);
         if (on && v0) p0[r] = c[u][0];
         if (on && v1) p1[r] = c[u][1];
-        c[u][0] = cn[u][0]; c[u][1] = cn[u][1]; x0[u] = xn0[u]; x1[u] = xn1[u];
       }
     }
   }
@@ -364,16 +351,17 @@ template <int N> __device__ __forceinline__ void warp_sum_n(double (&v)[N]) {
 template <int BR>
 __device__ __forceinline__ void panel_factor(double* S, double* Vp, double* Tsm, double* tau_s, double* Tglob, double* scratch,
                                              int c0, int pb, int warp, int lane) {
-  static_assert(BR == 32 * BQ_WARPS, "one 32-row slab per warp");
+  static_assert(BR == 32 * BQ_ROW_WARPS, "one 32-row slab per row warp");
+  const bool roww = warp < BQ_ROW_WARPS;          // warps 8..15 only take part in the barriers
   constexpr int LDS = BR + 4;
   double* red = scratch;            // [2][8 values][8 warps]
   double* drow = scratch + 128;     // [2][8]
   double* Gs = scratch + 144;       // [8 warps][64]
   double* Gtot = scratch + 656;     // [64]
-  const int i = 32 * warp + lane;
+  const int i = roww ? 32 * warp + lane : 0;
   double a[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) a[c] = (c < pb) ? S[(size_t)(c0 + c) * LDS + i] : 0.0;
+  for (int c = 0; c < 8; ++c) a[c] = (c < pb && roww) ? S[(size_t)(c0 + c) * LDS + i] : 0.0;
   double tau[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
@@ -381,23 +369,26 @@ __device__ __forceinline__ void panel_factor(double* S, double* Vp, double* Tsm,
     if (r < pb) {
       const int d = c0 + r;
       const int b = r & 1;
-      double p[8];
+      if (roww) {
+        double p[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) p[c] = (c >= r && i > d) ? a[r] * a[c] : 0.0;
+        for (int c = 0; c < 8; ++c) p[c] = (c >= r && i > d) ? a[r] * a[c] : 0.0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+        for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) if (c >= r) p[c] += __shfl_xor_sync(0xffffffffu, p[c], o);
-      }
-      if (lane == 0) {
+          for (int c = 0; c < 8; ++c) if (c >= r) p[c] += __shfl_xor_sync(0xffffffffu, p[c], o);
+        }
+        if (lane == 0) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) if (c >= r) red[b * 64 + c * 8 + warp] = p[c];
-      }
-      if (i == d) {
+          for (int c = 0; c < 8; ++c) if (c >= r) red[b * 64 + c * 8 + warp] = p[c];
+        }
+        if (i == d) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) drow[b * 8 + c] = a[c];
+          for (int c = 0; c < 8; ++c) drow[b * 8 + c] = a[c];
+        }
       }
       __syncthreads();
+      if (!roww) continue;
       double tot[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -435,15 +426,17 @@ __device__ __forceinline__ void panel_factor(double* S, double* Vp, double* Tsm,
     }
   }
   // storage form back to S; clean reflectors to Vp
+  if (roww) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if (c < pb) S[(size_t)(c0 + c) * LDS + i] = a[c];
-    const int d = c0 + c;
-    Vp[(size_t)c * LDS + i] = (c < pb) ? ((i > d) ? a[c] : (i == d ? 1.0 : 0.0)) : 0.0;
+    for (int c = 0; c < 8; ++c) {
+      if (c < pb) S[(size_t)(c0 + c) * LDS + i] = a[c];
+      const int d = c0 + c;
+      Vp[(size_t)c * LDS + i] = (c < pb) ? ((i > d) ? a[c] : (i == d ? 1.0 : 0.0)) : 0.0;
+    }
   }
   __syncthreads();
   // Gram partial of this warp's 32 rows on the tensor cores: G = V^T V (A and B fragments are the same values)
-  {
+  if (roww) {
     const int g = lane >> 2, t = lane & 3;
     double acc[2] = {0.0, 0.0};
     if (32 * warp + 31 >= c0) {
@@ -458,7 +451,7 @@ __device__ __forceinline__ void panel_factor(double* S, double* Vp, double* Tsm,
   if (threadIdx.x < 64) {
     double s2 = 0.0;
 #pragma unroll
-    for (int w = 0; w < BQ_WARPS; ++w) s2 += Gs[w * 64 + threadIdx.x];
+    for (int w = 0; w < BQ_ROW_WARPS; ++w) s2 += Gs[w * 64 + threadIdx.x];
     Gtot[threadIdx.x] = s2;
   }
   __syncthreads();
@@ -490,7 +483,7 @@ __device__ __forceinline__ void panel_factor(double* S, double* Vp, double* Tsm,
 template <int BR>
 __global__ void __launch_bounds__(BQ_THREADS, 1)
 k_house_factor_blk(double* __restrict__ Y, long long ldy, long long rows, int l, double* __restrict__ tau_g,
-                   double* __restrict__ Rstack, long long ldr, double* __restrict__ Tg) {
+                   double* __restrict__ Rstack, long long ldr, double* __restrict__ Tg, int dbg) {
   constexpr int LDS = BR + 4;
   extern __shared__ double sm[];
   double* S = sm;
@@ -511,9 +504,9 @@ k_house_factor_blk(double* __restrict__ Y, long long ldy, long long rows, int l,
   double* Tblock = Tg + (size_t)blockIdx.x * npanels * 64;
   for (int p = 0; p < npanels; ++p) {
     const int c0 = 8 * p, pb = min(8, l - c0);
-    panel_factor<BR>(S, Vp, Tsm, tau_s, Tblock + (size_t)p * 64, scratch, c0, pb, warp, lane);
+    if (!(dbg & 2)) panel_factor<BR>(S, Vp, Tsm, tau_s, Tblock + (size_t)p * 64, scratch, c0, pb, warp, lane);
     __syncthreads();
-    if (c0 + pb < l) block_reflect<BR>(S, Vp, Tsm, c0, c0 + pb, l, warp, BQ_WARPS, lane, true);
+    if (c0 + pb < l && !(dbg & 1)) block_reflect<BR>(S, Vp, Tsm, c0, c0 + pb, l, warp, BQ_WARPS, lane, true);
     __syncthreads();
   }
   double* Rb = Rstack + (size_t)blockIdx.x * l;
@@ -528,10 +521,14 @@ k_house_factor_blk(double* __restrict__ Y, long long ldy, long long rows, int l,
   for (int j = threadIdx.x; j < l; j += BQ_THREADS) tau_g[(size_t)blockIdx.x * l + j] = tau_s[j];
 }
 
+// Up to 16 tree levels can be processed by one launch (their blocks are independent when every level starts from the
+// identity): the block looks its level up in this table.
+struct ApplyLevel { const double* V; long long ldv; long long rows; const double* Tg; const double* Ctop; long long ldc; double* Q; long long ldq; int first_block; };
+struct ApplyTable { ApplyLevel lv[16]; int n; };
+
 template <int BR>
 __global__ void __launch_bounds__(BQ_THREADS, 1)
-k_house_apply_blk(const double* V, long long ldv, long long rows, int l, const double* __restrict__ Tg,
-                  const double* __restrict__ Ctop, long long ldc, double* Q, long long ldq) {
+k_house_apply_blk(const ApplyTable tab, int l) {
   constexpr int LDS = BR + 4;
   constexpr int VPT = 8 * BR / BQ_THREADS;       // staged reflector values per thread
   extern __shared__ double sm[];
@@ -539,18 +536,24 @@ k_house_apply_blk(const double* V, long long ldv, long long rows, int l, const d
   double* Vp = S + (size_t)l * LDS;
   double* Tsm = Vp + (size_t)8 * LDS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long r0 = (long long)blockIdx.x * BR;
+  int li = 0;
+  while (li + 1 < tab.n && (int)blockIdx.x >= tab.lv[li + 1].first_block) ++li;
+  const double* V = tab.lv[li].V; const long long ldv = tab.lv[li].ldv; const long long rows = tab.lv[li].rows;
+  const double* Tg = tab.lv[li].Tg; const double* Ctop = tab.lv[li].Ctop; const long long ldc = tab.lv[li].ldc;
+  double* Q = tab.lv[li].Q; const long long ldq = tab.lv[li].ldq;
+  const int blk = (int)blockIdx.x - tab.lv[li].first_block;
+  const long long r0 = (long long)blk * BR;
   const int nrows = (int)min((long long)BR, rows - r0);
   const int npanels = (l + 7) / 8;
 
   for (int k = warp; k < l; k += BQ_WARPS) {
     for (int i = lane; i < BR; i += 32) {
       double c = 0.0;
-      if (i < l) c = Ctop ? Ctop[(size_t)k * ldc + (size_t)blockIdx.x * l + i] : (i == k ? 1.0 : 0.0);
+      if (i < l) c = Ctop ? Ctop[(size_t)k * ldc + (size_t)blk * l + i] : (i == k ? 1.0 : 0.0);
       S[(size_t)k * LDS + i] = c;
     }
   }
-  const double* Tblock = Tg + (size_t)blockIdx.x * npanels * 64;
+  const double* Tblock = Tg + (size_t)blk * npanels * 64;
   // stage panel p: thread e handles elements e, e + 256, ... of the 8 x BR panel (column-major)
   double vreg[VPT];
   auto fetch = [&](int p) {
@@ -581,6 +584,53 @@ k_house_apply_blk(const double* V, long long ldv, long long rows, int l, const d
   for (int k = warp; k < l; k += BQ_WARPS) {
     double* dst = Q + (size_t)k * ldq + r0;
     for (int i = lane; i < nrows; i += 32) dst[i] = S[(size_t)k * LDS + i];
+  }
+}
+
+// Out (rows x l) = blockwise N * C:  rows [b*BR, (b+1)*BR) of N are multiplied by the l x l block C_b = rows [b*l, (b+1)*l) of
+// Cpar (ldc).  One CTA per (node b, 64-row chunk).  Used to chain the explicit node factors of the upper tree levels.
+constexpr int NG_ROWS = 64;
+__global__ void __launch_bounds__(256)
+k_node_gemm(const double* __restrict__ N, long long ldn, long long rows, int l, int BR, const double* __restrict__ Cpar, long long ldc,
+            double* __restrict__ Out, long long ldo) {
+  extern __shared__ double sm[];
+  double* Cs = sm;                          // l x l, column-major, ld = l
+  double* Ns = sm + (size_t)l * l;          // NG_ROWS x l, stored [k][row] with ld = NG_ROWS + 1
+  const int chunks = BR / NG_ROWS;
+  const int b = blockIdx.x / chunks, ch = blockIdx.x % chunks;
+  const long long r0 = (long long)b * BR + (long long)ch * NG_ROWS;
+  if (r0 >= rows) return;
+  const int nr = (int)min((long long)NG_ROWS, rows - r0);
+  for (int e = threadIdx.x; e < l * l; e += 256) { const int i = e % l, k = e / l; Cs[e] = Cpar[(size_t)k * ldc + (size_t)b * l + i]; }
+  for (int e = threadIdx.x; e < NG_ROWS * l; e += 256) {
+    const int i = e % NG_ROWS, k = e / NG_ROWS;
+    Ns[(size_t)k * (NG_ROWS + 1) + i] = (i < nr) ? N[(size_t)k * ldn + r0 + i] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // rows 4*ty .. 4*ty+3, columns tx + 16*j
+  double acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  for (int k = 0; k < l; ++k) {
+    double a[4], bb[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = Ns[(size_t)k * (NG_ROWS + 1) + 4 * ty + i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int c = tx + 16 * j; bb[j] = (c < l) ? Cs[(size_t)c * l + k] : 0.0; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = tx + 16 * j;
+    if (c < l) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const int r = 4 * ty + i; if (r < nr) Out[(size_t)c * ldo + r0 + r] = acc[i][j]; }
+    }
   }
 }
 
@@ -680,6 +730,8 @@ int pick_br(int l) {
   return 0;
 }
 
+int dbg_mode() { static int m = -1; if (m < 0) { const char* e = getenv("RSVDB_TSQR_DEBUG"); m = e ? atoi(e) : 0; } return m; }   // timing experiments only
+
 size_t blk_smem_bytes(int l) { return ((size_t)(l + 8) * (256 + 4) + 64 + 720 + (size_t)l) * sizeof(double); }
 
 cudaError_t set_attr_blk_once() {
@@ -714,7 +766,7 @@ cudaError_t Tsqr::plan(long long rows, int l) {
   size_t need = 0;
   long long r = rows;
   if (br_ == 0 || r <= 0) {           // single global-memory leaf
-    Level L; L.rows = r; L.nb = 1; L.off_R = need; need += (size_t)l * l; L.off_tau = need; need += (size_t)l; L.off_T = need;
+    Level L; L.rows = r; L.nb = 1; L.off_R = need; need += (size_t)l * l; L.off_tau = need; need += (size_t)l; L.off_T = need; L.off_E = need;
     levels_.push_back(L);
     off_top_ = need; need += (size_t)l * l;
     off_scratch_ = need; need += (size_t)std::max<long long>(r, 1) * l;   // apply_global cannot run in place
@@ -724,6 +776,7 @@ cudaError_t Tsqr::plan(long long rows, int l) {
       L.off_R = need; need += (size_t)L.nb * l * l;
       L.off_tau = need; need += (size_t)L.nb * l;
       L.off_T = need; if (blk_) need += (size_t)L.nb * ((l + 7) / 8) * 64;
+      L.off_E = need; if (blk_ && !levels_.empty()) need += (size_t)r * l;       // chained explicit factor of this (upper) level
       levels_.push_back(L);
       if (L.nb == 1) break;
       r = (long long)L.nb * l;
@@ -750,7 +803,7 @@ cudaError_t Tsqr::factor(cudaStream_t st, double* Y, long long ldy, int* launche
     cudaError_t e;
     if (blk_) {
       e = set_attr_blk_once(); if (e != cudaSuccess) return e;
-      k_house_factor_blk<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
+      k_house_factor_blk<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T, dbg_mode());
     } else
     switch (br_) {
       case 512: e = set_attr_once<512>(); if (e != cudaSuccess) return e;
@@ -785,6 +838,52 @@ cudaError_t Tsqr::form_q(cudaStream_t st, double* Y, long long ldy, const double
     if (launches) *launches += 2;
     return cudaSuccess;
   }
+  if (blk_) {
+    const int nlev = (int)levels_.size();
+    const size_t smem = blk_smem_bytes(l_);
+    auto level_V = [&](int i, double** V, long long* ldv) {
+      if (i == 0) { *V = Y; *ldv = ldy; } else { *V = base + levels_[i - 1].off_R; *ldv = (long long)levels_[i - 1].nb * l_; }
+    };
+    const double* Cleaf = Ctop; long long ldcleaf = ldc;
+    if (nlev > 1) {
+      if (nlev - 1 > 16) return cudaErrorInvalidValue;
+      // (A) explicit factor N_i = H [I; 0] of every upper level in ONE launch (in place over the reflectors)
+      ApplyTable tab; tab.n = 0; int first = 0;
+      for (int i = 1; i < nlev; ++i) {
+        double* V; long long ldv; level_V(i, &V, &ldv);
+        ApplyLevel& a = tab.lv[tab.n++];
+        a.V = V; a.ldv = ldv; a.rows = levels_[i].rows; a.Tg = base + levels_[i].off_T; a.Ctop = nullptr; a.ldc = 0; a.Q = V; a.ldq = ldv;
+        a.first_block = first; first += levels_[i].nb;
+      }
+      k_house_apply_blk<256><<<first, BQ_THREADS, smem, st>>>(tab, l_);
+      cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+      if (launches) ++*launches;
+      // (B) chain top-down: E_i[node b] = N_i[node b] * E_{i+1}[rows b*l .. (b+1)*l)   (E_top = N_top * Ctop)
+      static bool ng_attr = false;
+      const size_t ng_smem = ((size_t)l_ * l_ + (size_t)l_ * (NG_ROWS + 1)) * sizeof(double);
+      if (!ng_attr) { e = cudaFuncSetAttribute(k_node_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; ng_attr = true; }
+      const double* Epar = Ctop; long long ldpar = ldc;
+      for (int i = nlev - 1; i >= 1; --i) {
+        double* V; long long ldv; level_V(i, &V, &ldv);
+        if (Epar) {
+          double* E = base + levels_[i].off_E;
+          k_node_gemm<<<levels_[i].nb * (256 / NG_ROWS), 256, ng_smem, st>>>(V, ldv, levels_[i].rows, l_, 256, Epar, ldpar, E, levels_[i].rows);
+          e = cudaGetLastError(); if (e != cudaSuccess) return e;
+          if (launches) ++*launches;
+          Epar = E; ldpar = levels_[i].rows;
+        } else { Epar = V; ldpar = ldv; }                        // top level with the identity on top: E_top = N_top
+      }
+      Cleaf = Epar; ldcleaf = ldpar;
+    }
+    // (C) leaves
+    ApplyTable tab; tab.n = 1;
+    tab.lv[0].V = Y; tab.lv[0].ldv = ldy; tab.lv[0].rows = levels_[0].rows; tab.lv[0].Tg = base + levels_[0].off_T;
+    tab.lv[0].Ctop = Cleaf; tab.lv[0].ldc = ldcleaf; tab.lv[0].Q = Y; tab.lv[0].ldq = ldy; tab.lv[0].first_block = 0;
+    k_house_apply_blk<256><<<levels_[0].nb, BQ_THREADS, smem, st>>>(tab, l_);
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+    return cudaSuccess;
+  }
   for (int i = (int)levels_.size() - 1; i >= 0; --i) {
     Level& L = levels_[i];
     double* V; long long ldv;
@@ -792,9 +891,6 @@ cudaError_t Tsqr::form_q(cudaStream_t st, double* Y, long long ldy, const double
     const double* C; long long ldcc;
     if (i == (int)levels_.size() - 1) { C = Ctop; ldcc = ldc; } else { C = base + L.off_R; ldcc = (long long)L.nb * l_; }
     const size_t smem = ((size_t)br_ * l_ + l_) * sizeof(double);
-    if (blk_) {
-      k_house_apply_blk<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(V, ldv, L.rows, l_, base + L.off_T, C, ldcc, V, ldv);
-    } else
     switch (br_) {
       case 512: k_house_apply<512><<<L.nb, QR_THREADS, smem, st>>>(V, ldv, L.rows, l_, base + L.off_tau, C, ldcc, V, ldv); break;
       case 256: k_house_apply<256><<<L.nb, QR_THREADS, smem, st>>>(V, ldv, L.rows, l_, base + L.off_tau, C, ldcc, V, ldv); break;
