@@ -23,9 +23,12 @@ __device__ __forceinline__ double wsum(double v) {
   return v;
 }
 
-constexpr int JMAX_RPL = 16;   // rows per lane: k <= 512
+constexpr int JMAX_RPL = 32;   // rows per lane of a 16-lane group: k <= 512
 
 // X, Z: k x k column-major with leading dimension k, in shared or global memory.
+// One column pair per HALF warp (16 lanes, RPL rows per lane): with 1024 threads all k/2 <= 64 pairs of a round-robin
+// step rotate at once.  The rotation angle comes from two rsqrt (no FP64 division or square root on the critical path):
+//   d = b - a, r = sqrt(d^2 + 4 g^2), cos(2t) = |d| / r, c = sqrt((1 + cos 2t) / 2), s = sign(d) g / (r c).
 template <int RPL>
 __global__ void __launch_bounds__(1024, 1)
 k_jacobi(const double* __restrict__ W, long long ldw, int k, int transpose_in, double* __restrict__ Uo, long long ldu,
@@ -38,6 +41,7 @@ k_jacobi(const double* __restrict__ W, long long ldw, int k, int transpose_in, d
   double* Z = use_smem ? sm + (size_t)k * k : Zg;
   double* sig = use_smem ? sm + 2 * (size_t)k * k : Zg + (size_t)k * k;   // k doubles
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int hl = tid & 15, grp = tid >> 4, ngrp = blockDim.x >> 4;         // half-warp lane / group
 
   for (int e = tid; e < k * k; e += blockDim.x) {
     const int i = e % k, j = e / k;
@@ -50,36 +54,47 @@ k_jacobi(const double* __restrict__ W, long long ldw, int k, int transpose_in, d
   const int n = (k + 1) & ~1;          // players in the round-robin (one dummy when k is odd)
   const int npairs = n >> 1;
   const double tol = sqrt((double)k) * (0.5 * DBL_EPSILON);
+  const double tol2 = tol * tol;
   int sweep = 0; bool converged = (k < 2);
   while (!converged && sweep < max_sweeps) {
     if (tid == 0) s_rot = 0;
     __syncthreads();
     for (int step = 0; step < n - 1; ++step) {
       int nrot = 0;
-      for (int pi = warp; pi < npairs; pi += nwarps) {
-        int p, q;
-        if (pi == 0) { p = n - 1; q = step; }
-        else { p = (step + pi) % (n - 1); q = (step - pi + (n - 1)) % (n - 1); }
-        if (p > q) { const int t = p; p = q; q = t; }
-        if (q >= k) continue;           // dummy player
-        double* xp = X + (size_t)p * k; double* xq = X + (size_t)q * k;
+      for (int pi = grp; pi < ((npairs + ngrp - 1) / ngrp) * ngrp; pi += ngrp) {   // uniform trip count per half warp pair
+        int p = 0, q = k;
+        if (pi < npairs) {
+          if (pi == 0) { p = n - 1; q = step; }
+          else { p = (step + pi) % (n - 1); q = (step - pi + (n - 1)) % (n - 1); }
+          if (p > q) { const int t = p; p = q; q = t; }
+        }
+        const bool live = q < k;        // not the dummy player, not a padding pair
+        double* xp = X + (size_t)(live ? p : 0) * k; double* xq = X + (size_t)(live ? q : 0) * k;
         double a = 0.0, b = 0.0, g = 0.0, vp[RPL], vq[RPL];
 #pragma unroll
         for (int ii = 0; ii < RPL; ++ii) {
-          const int i = lane + 32 * ii;
-          vp[ii] = (i < k) ? xp[i] : 0.0; vq[ii] = (i < k) ? xq[i] : 0.0;
+          const int i = hl + 16 * ii;
+          const bool on = live && i < k;
+          vp[ii] = on ? xp[i] : 0.0; vq[ii] = on ? xq[i] : 0.0;
           a = fma(vp[ii], vp[ii], a); b = fma(vq[ii], vq[ii], b); g = fma(vp[ii], vq[ii], g);
         }
-        a = wsum(a); b = wsum(b); g = wsum(g);
-        if (fabs(g) > tol * sqrt(a * b) && fabs(g) > DBL_MIN) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); g += __shfl_xor_sync(0xffffffffu, g, o);
+        }
+        if (live && g * g > tol2 * (a * b) && fabs(g) > DBL_MIN) {
           ++nrot;
-          const double zeta = (b - a) / (2.0 * g);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+          const double d = b - a;
+          const double n2 = fma(d, d, 4.0 * g * g);
+          const double ir = rsqrt(n2);                       // 1 / r
+          const double c2 = fma(0.5 * fabs(d), ir, 0.5);     // cos^2 = (1 + |d| / r) / 2   in [0.5, 1]
+          const double ic = rsqrt(c2);
+          const double c = c2 * ic;
+          const double s = ((d >= 0.0) ? g : -g) * ir * ic;
           double* zp = Z + (size_t)p * k; double* zq = Z + (size_t)q * k;
 #pragma unroll
           for (int ii = 0; ii < RPL; ++ii) {
-            const int i = lane + 32 * ii;
+            const int i = hl + 16 * ii;
             if (i < k) {
               xp[i] = c * vp[ii] - s * vq[ii];
               xq[i] = s * vp[ii] + c * vq[ii];
@@ -90,7 +105,7 @@ k_jacobi(const double* __restrict__ W, long long ldw, int k, int transpose_in, d
           }
         }
       }
-      if (nrot && lane == 0) atomicAdd(&s_rot, nrot);
+      if (nrot && hl == 0) atomicAdd(&s_rot, nrot);
       __syncthreads();
     }
     ++sweep;
@@ -129,7 +144,7 @@ k_jacobi(const double* __restrict__ W, long long ldw, int k, int transpose_in, d
 cudaError_t jacobi_svd_square(GemmWorkspace& ws, cudaStream_t st, const double* W, long long ldw, int k, int transpose_in,
                               double* U, long long ldu, double* S, double* Z, long long ldz, int* d_info, int* launches) {
   if (k <= 0) return cudaSuccess;
-  if (k > 32 * JMAX_RPL) return cudaErrorInvalidValue;
+  if (k > 16 * JMAX_RPL) return cudaErrorInvalidValue;
   const size_t smem_need = (2 * (size_t)k * k + k) * sizeof(double);
   const int use_smem = smem_need <= 220 * 1024;
   double* Xg = nullptr; double* Zg = nullptr;
@@ -139,13 +154,14 @@ cudaError_t jacobi_svd_square(GemmWorkspace& ws, cudaStream_t st, const double* 
   }
   const size_t smem = use_smem ? smem_need : 0;
   const int threads = k >= 48 ? 1024 : (k >= 24 ? 512 : 256);
-  const int rpl = (k + 31) / 32;
+  const int rpl = (k + 15) / 16;
 #define JLAUNCH(R)                                                                                                   \
   { static bool attr = false;                                                                                        \
     if (!attr) { cudaError_t e = cudaFuncSetAttribute(k_jacobi<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
                  if (e != cudaSuccess) return e; attr = true; }                                                      \
     k_jacobi<R><<<1, threads, smem, st>>>(W, ldw, k, transpose_in, U, ldu, S, Z, ldz, Xg, Zg, use_smem, 60, d_info); }
-  if (rpl <= 1) JLAUNCH(1) else if (rpl <= 2) JLAUNCH(2) else if (rpl <= 4) JLAUNCH(4) else if (rpl <= 8) JLAUNCH(8) else JLAUNCH(16)
+  if (rpl <= 1) JLAUNCH(1) else if (rpl <= 2) JLAUNCH(2) else if (rpl <= 4) JLAUNCH(4) else if (rpl <= 7) JLAUNCH(7) else if (rpl <= 8) JLAUNCH(8)
+  else if (rpl <= 16) JLAUNCH(16) else JLAUNCH(32)
 #undef JLAUNCH
   if (launches) ++*launches;
   return cudaGetLastError();
