@@ -54,15 +54,16 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi clocks / throttle reasons under load (B200_PROFILING.md).  The sampler runs from the warm-up steps to
+    the end of the timed steps (same kernels, same load); samples taken while the GPU is busy (utilization >= 50 %) count."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
@@ -80,13 +81,20 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             pass
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
-        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
+        def num(x):
+            try:
+                return float(x)
+            except Exception:
+                return None
+        rows = [r for r in self.rows if len(r) >= 9 and num(r[1]) is not None]
+        busy = [r for r in rows if (num(r[4]) or 0) >= 50] or rows
+        sm = sorted(num(r[1]) for r in busy)
+        mx = [num(r[2]) for r in rows if num(r[2]) is not None]
+        pw = [num(r[3]) for r in busy if num(r[3]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(len(r) >= 8 and r[4 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [nm for i, nm in enumerate(names) if any(r[5 + i].lower().startswith("active") for r in busy)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
-                "samples": len(sm), "reasons": reasons}
+                "samples": len(rows), "samples_under_load": len(busy) if busy is not rows else 0, "reasons": reasons}
 
 
 def flops(m, n, l, q):
@@ -182,11 +190,11 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     eng.set_profiling(True); eng.phase_ms()
-    sampler = ClockSampler(local); sampler.start()
     launches0 = eng.launches
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
