@@ -480,6 +480,326 @@ __device__ __forceinline__ void panel_factor(double* S, double* Vp, double* Tsm,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Look-ahead factor kernel.  The 16 warps form two teams: the ROW team (warps 0-7, one 32-row slab each) updates the
+// NEXT panel's 8 columns with the current panel's reflectors (cooperatively: per-slab partial V^T C on the tensor
+// cores, summed through shared memory) and factors that panel right away, while the UPDATE team (warps 8-15) applies
+// the current panel to the remaining columns.  The reflector chain of panel p+1 thus overlaps the trailing update of
+// panel p; the teams meet at one block barrier per panel, the row team synchronises internally on named barrier 1.
+// Reflectors are read in place from S (plus a clean 8 x 8 top block), double-buffered together with T.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// clean reflector value V[row][r] of the panel starting at column / row c0 (rows in [c0, c0+8) come from Vtop)
+template <int BR>
+__device__ __forceinline__ double clean_v(const double* S, const double* Vtop, int c0, int row, int r) {
+  constexpr int LDS = BR + 4;
+  if (row < c0) return 0.0;
+  if (row < c0 + 8) return Vtop[r * 8 + (row - c0)];
+  return S[(size_t)(c0 + r) * LDS + row];
+}
+
+// Row team: factor the panel [c0, c0+pb) (thread = one row).  Writes S (storage form), Vtop, Tsm, Tglob, tau_s.
+template <int BR>
+__device__ __forceinline__ void panel_factor_la(double* S, double* Vtop, double* Tsm, double* tau_s, double* Tglob, double* scratch,
+                                                int c0, int pb, int warp, int lane) {
+  constexpr int LDS = BR + 4;
+  double* red = scratch;            // [2][8 values][8 warps]
+  double* drow = scratch + 128;     // [2][8]
+  double* Gs = scratch + 144;       // [8 warps][64]
+  double* Gtot = scratch + 656;     // [64]
+  const int i = 32 * warp + lane;
+  double a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = (c < pb) ? S[(size_t)(c0 + c) * LDS + i] : 0.0;
+  double tau[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    tau[r] = 0.0;
+    if (r < pb) {
+      const int d = c0 + r;
+      const int b = r & 1;
+      double p[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) p[c] = (c >= r && i > d) ? a[r] * a[c] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) if (c >= r) p[c] += __shfl_xor_sync(0xffffffffu, p[c], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) if (c >= r) red[b * 64 + c * 8 + warp] = p[c];
+      }
+      if (i == d) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) drow[b * 8 + c] = a[c];
+      }
+      bar_rows();
+      double tot[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        tot[c] = 0.0;
+        if (c >= r) {
+          const double2* q = reinterpret_cast<const double2*>(red + b * 64 + c * 8);
+          const double2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+          tot[c] = ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
+        }
+      }
+      const double tail = tot[r], x0 = drow[b * 8 + r];
+      double beta, scale;
+      if (tail <= DBL_MIN) { tau[r] = 0.0; beta = x0; scale = 0.0; }
+      else {
+        const double n2 = fma(x0, x0, tail);
+        const double inrm = rsqrt(n2);
+        const double nrm = n2 * inrm;
+        const double ax = fabs(x0);
+        beta = (x0 >= 0.0) ? -nrm : nrm;
+        tau[r] = fma(ax, inrm, 1.0);
+        const double rc = __drcp_rn(ax + nrm);
+        scale = (x0 >= 0.0) ? rc : -rc;
+      }
+      const double v = (i > d) ? a[r] * scale : (i == d ? 1.0 : 0.0);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c > r && c < pb) {
+          const double w = tau[r] * fma(scale, tot[c], drow[b * 8 + c]);
+          a[c] = fma(-w, v, a[c]);
+        }
+      }
+      if (i > d) a[r] = v; else if (i == d) a[r] = beta;
+    }
+  }
+  // storage form back to S; clean top block (rows c0 .. c0+7) to Vtop
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (c < pb) S[(size_t)(c0 + c) * LDS + i] = a[c];
+    if (i >= c0 && i < c0 + 8) {
+      const int d = c0 + c;
+      Vtop[c * 8 + (i - c0)] = (c < pb) ? ((i > d) ? a[c] : (i == d ? 1.0 : 0.0)) : 0.0;
+    }
+  }
+  __syncwarp();
+  // Gram partial of this warp's 32 rows: G = V^T V on the tensor cores (each warp reads only rows it wrote itself)
+  {
+    const int g = lane >> 2, t = lane & 3;
+    double acc[2] = {0.0, 0.0};
+    if (32 * warp + 31 >= c0 && g < pb) {
+      // (columns g >= pb do not exist: their clean reflector is zero)
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < 32; k0 += 4) {
+      const int row = 32 * warp + k0 + t;
+      const double x = (g < pb) ? clean_v<BR>(S, Vtop, c0, row, g) : 0.0;
+      dmma884(acc, x, x);
+    }
+    Gs[warp * 64 + g + 8 * (2 * t)] = acc[0];
+    Gs[warp * 64 + g + 8 * (2 * t + 1)] = acc[1];
+  }
+  bar_rows();
+  if (threadIdx.x < 64) {
+    double s2 = 0.0;
+#pragma unroll
+    for (int w = 0; w < BQ_ROW_WARPS; ++w) s2 += Gs[w * 64 + threadIdx.x];
+    Gtot[threadIdx.x] = s2;
+  }
+  bar_rows();
+  if (threadIdx.x < 8) {
+    const int srow = threadIdx.x;
+    double trow[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      double val = 0.0;
+      if (c == srow) val = tau[c];
+      else if (c > srow) {
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < c && r >= srow) acc = fma(trow[r], Gtot[r + 8 * c], acc);
+        val = -tau[c] * acc;
+      }
+      trow[c] = val;
+      Tsm[srow + 8 * c] = val;
+      Tglob[srow + 8 * c] = val;
+    }
+    double tv = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c == srow) tv = tau[c];
+    if (srow < pb) tau_s[c0 + srow] = tv;
+  }
+}
+
+// Row team: apply the reflectors of the panel at c0 to the 8 columns starting at n0 (the next panel), slab by slab.
+template <int BR>
+__device__ __forceinline__ void coop_update(double* S, const double* Vtop, const double* Tsm, double* Ws, int c0, int n0, int col_end,
+                                            int warp, int lane) {
+  constexpr int LDS = BR + 4;
+  const int g = lane >> 2, t = lane & 3;
+  const int rbase = 32 * warp;
+  const bool any = rbase + 31 >= c0;
+  const int colB = n0 + perm8(g);
+  const bool bval = colB < col_end;
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  if (any) {
+    const double* cb = S + (size_t)(bval ? colB : n0) * LDS + rbase + t;
+#pragma unroll
+    for (int k0 = 0; k0 < 32; k0 += 4) {
+      const double av = clean_v<BR>(S, Vtop, c0, rbase + k0 + t, g);
+      const double bv = bval ? cb[k0] : 0.0;
+      dmma884(acc[(k0 >> 2) & 1], av, bv);
+    }
+  }
+  Ws[warp * 64 + g + 8 * (2 * t)] = acc[0][0] + acc[1][0];
+  Ws[warp * 64 + g + 8 * (2 * t + 1)] = acc[0][1] + acc[1][1];
+  bar_rows();
+  if (!any) return;
+  double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+  for (int w = 0; w < BQ_ROW_WARPS; ++w) { w0 += Ws[w * 64 + g + 8 * (2 * t)]; w1 += Ws[w * 64 + g + 8 * (2 * t + 1)]; }
+  const double bw0 = frag_c_to_b(w0, w1, t, g), bw1 = frag_c_to_b(w0, w1, t + 4, g);
+  double x[2] = {0.0, 0.0};
+  dmma884(x, Tsm[t + 8 * g], bw0);                 // X = T^T W
+  dmma884(x, Tsm[(t + 4) + 8 * g], bw1);
+  const double bx0 = -frag_c_to_b(x[0], x[1], t, g), bx1 = -frag_c_to_b(x[0], x[1], t + 4, g);
+  const int col0 = n0 + perm8(2 * t), col1 = n0 + perm8(2 * t + 1);
+  const bool v0 = col0 < col_end, v1 = col1 < col_end;
+  double* p0 = S + (size_t)(v0 ? col0 : n0) * LDS + g;
+  double* p1 = S + (size_t)(v1 ? col1 : n0) * LDS + g;
+  double c[4][2], xa[4], xb[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r0 = rbase + 8 * u;
+    const bool on = r0 + 7 >= c0;                  // c0 is a multiple of 8: the block is entirely below or entirely at/after c0
+    c[u][0] = (on && v0) ? p0[r0] : 0.0; c[u][1] = (on && v1) ? p1[r0] : 0.0;
+    xa[u] = on ? clean_v<BR>(S, Vtop, c0, r0 + g, t) : 0.0;
+    xb[u] = on ? clean_v<BR>(S, Vtop, c0, r0 + g, t + 4) : 0.0;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) dmma884(c[u], xa[u], bx0);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) dmma884(c[u], xb[u], bx1);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r0 = rbase + 8 * u;
+    const bool on = r0 + 7 >= c0;
+    if (on && v0) p0[r0] = c[u][0];
+    if (on && v1) p1[r0] = c[u][1];
+  }
+}
+
+// Update team: block_reflect with the reflectors read in place from S (+ Vtop for the panel's first 8 rows).
+template <int BR>
+__device__ __forceinline__ void block_reflect_s(double* S, const double* Vtop, const double* Tsm, int c0, int col_begin, int col_end,
+                                                int warp, int nwarps, int lane) {
+  constexpr int LDS = BR + 4;
+  const int g = lane >> 2, t = lane & 3;
+  for (int n0 = col_begin + 8 * warp; n0 < col_end; n0 += 8 * nwarps) {
+    double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    const int colB = n0 + perm8(g);
+    const bool bval = colB < col_end;
+    const double* cb = S + (size_t)(bval ? colB : col_begin) * LDS + c0 + t;
+    const double* va = S + (size_t)(c0 + g) * LDS + c0 + t;          // rows >= c0 + 8
+    const double* vt = Vtop + g * 8 + t;                             // rows c0 .. c0+7
+    const int nk = (BR - c0) >> 2;
+    for (int k = 0; k < nk; k += 4) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = k + u; const bool on = kk < nk;
+        av[u] = on ? (kk < 2 ? vt[4 * kk] : va[4 * kk]) : 0.0;
+        bv[u] = (on && bval) ? cb[4 * kk] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dmma884(acc[u], av[u], bv[u]);
+    }
+    const double w0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+    const double w1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+    const double bw0 = frag_c_to_b(w0, w1, t, g), bw1 = frag_c_to_b(w0, w1, t + 4, g);
+    double x[2] = {0.0, 0.0};
+    dmma884(x, Tsm[t + 8 * g], bw0);
+    dmma884(x, Tsm[(t + 4) + 8 * g], bw1);
+    const double bx0 = -frag_c_to_b(x[0], x[1], t, g), bx1 = -frag_c_to_b(x[0], x[1], t + 4, g);
+    const int col0 = n0 + perm8(2 * t), col1 = n0 + perm8(2 * t + 1);
+    const bool v0 = col0 < col_end, v1 = col1 < col_end;
+    double* p0 = S + (size_t)(v0 ? col0 : col_begin) * LDS + c0 + g;
+    double* p1 = S + (size_t)(v1 ? col1 : col_begin) * LDS + c0 + g;
+    const double* a0p = S + (size_t)(c0 + t) * LDS + c0 + g;
+    const double* a1p = S + (size_t)(c0 + t + 4) * LDS + c0 + g;
+    const int nblk = (BR - c0) >> 3;
+    for (int b0 = 0; b0 < nblk; b0 += 4) {
+      double c[4][2], x0[4], x1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int bb = b0 + u; const bool on = bb < nblk; const int r = 8 * bb;
+        c[u][0] = (on && v0) ? p0[r] : 0.0; c[u][1] = (on && v1) ? p1[r] : 0.0;
+        x0[u] = on ? (bb == 0 ? Vtop[t * 8 + g] : a0p[r]) : 0.0;
+        x1[u] = on ? (bb == 0 ? Vtop[(t + 4) * 8 + g] : a1p[r]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dmma884(c[u], x0[u], bx0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dmma884(c[u], x1[u], bx1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int bb = b0 + u; const bool on = bb < nblk; const int r = 8 * bb;
+        if (on && v0) p0[r] = c[u][0];
+        if (on && v1) p1[r] = c[u][1];
+      }
+    }
+  }
+}
+
+template <int BR>
+__global__ void __launch_bounds__(BQ_THREADS, 1)
+k_house_factor_la(double* __restrict__ Y, long long ldy, long long rows, int l, double* __restrict__ tau_g,
+                  double* __restrict__ Rstack, long long ldr, double* __restrict__ Tg) {
+  constexpr int LDS = BR + 4;
+  extern __shared__ double sm[];
+  double* S = sm;
+  double* Vtop = S + (size_t)l * LDS;              // [2][64]
+  double* Tsm = Vtop + 128;                        // [2][64]
+  double* scratch = Tsm + 128;                     // 720
+  double* Ws = scratch + 720;                      // [8][64]
+  double* tau_s = Ws + 512;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool roww = warp < BQ_ROW_WARPS;
+  const long long r0 = (long long)blockIdx.x * BR;
+  const int nrows = (int)min((long long)BR, rows - r0);
+  const int npanels = (l + 7) / 8;
+
+  for (int k = warp; k < l; k += BQ_WARPS) {
+    const double* src = Y + (size_t)k * ldy + r0;
+    for (int i = lane; i < BR; i += 32) S[(size_t)k * LDS + i] = (i < nrows) ? src[i] : 0.0;
+  }
+  __syncthreads();
+  double* Tblock = Tg + (size_t)blockIdx.x * npanels * 64;
+  if (roww) panel_factor_la<BR>(S, Vtop, Tsm, tau_s, Tblock, scratch, 0, min(8, l), warp, lane);
+  __syncthreads();
+  for (int p = 0; p < npanels; ++p) {
+    const int c0 = 8 * p, pb = min(8, l - c0), buf = p & 1;
+    const int n0 = c0 + pb;                        // first column of the next panel
+    if (roww) {
+      if (n0 < l) {
+        coop_update<BR>(S, Vtop + buf * 64, Tsm + buf * 64, Ws, c0, n0, min(l, n0 + 8), warp, lane);
+        __syncwarp();
+        panel_factor_la<BR>(S, Vtop + (buf ^ 1) * 64, Tsm + (buf ^ 1) * 64, tau_s, Tblock + (size_t)(p + 1) * 64, scratch, n0, min(8, l - n0), warp, lane);
+      }
+    } else {
+      if (n0 + 8 < l) block_reflect_s<BR>(S, Vtop + buf * 64, Tsm + buf * 64, c0, n0 + 8, l, warp - BQ_ROW_WARPS, BQ_WARPS - BQ_ROW_WARPS, lane);
+    }
+    __syncthreads();
+  }
+  double* Rb = Rstack + (size_t)blockIdx.x * l;
+  for (int k = warp; k < l; k += BQ_WARPS) {
+    double* dst = Y + (size_t)k * ldy + r0;
+    for (int i = lane; i < BR; i += 32) {
+      const double val = S[(size_t)k * LDS + i];
+      if (i < nrows) dst[i] = val;
+      if (i < l) Rb[(size_t)k * ldr + i] = (i <= k) ? val : 0.0;
+    }
+  }
+  for (int j = threadIdx.x; j < l; j += BQ_THREADS) tau_g[(size_t)blockIdx.x * l + j] = tau_s[j];
+}
+
 template <int BR>
 __global__ void __launch_bounds__(BQ_THREADS, 1)
 k_house_factor_blk(double* __restrict__ Y, long long ldy, long long rows, int l, double* __restrict__ tau_g,
@@ -741,6 +1061,8 @@ cudaError_t set_attr_blk_once() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_house_apply_blk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_house_factor_la<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
   done = true;
   return cudaSuccess;
 }
@@ -803,7 +1125,10 @@ cudaError_t Tsqr::factor(cudaStream_t st, double* Y, long long ldy, int* launche
     cudaError_t e;
     if (blk_) {
       e = set_attr_blk_once(); if (e != cudaSuccess) return e;
-      k_house_factor_blk<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T, dbg_mode());
+      if (dbg_mode() & 4)
+        k_house_factor_blk<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T, dbg_mode());
+      else
+        k_house_factor_la<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
     } else
     switch (br_) {
       case 512: e = set_attr_once<512>(); if (e != cudaSuccess) return e;

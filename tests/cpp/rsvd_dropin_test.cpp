@@ -66,6 +66,21 @@ int main(int argc, char** argv) {
   try { rSVD(A, U, S, V, l, static_cast<SVDMethod>(7)); } catch (const std::invalid_argument&) { threw += 2; }
   std::printf("invalid_argument paths: %d\n", threw);
 
+  // src/JacobiOperations.cpp:6-103 -- host-side rotation helpers keep the reference's arithmetic
+  {
+    Mat_m M(3, 3); double vals[9] = {4, 1, 2, 0.5, 3, 1, 0.25, 0.75, 2};
+    for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) M(i, j) = vals[i + 3 * j];
+    double cl, sl, cr, sr;
+    const bool real = svd_precondition_2x2_block_to_be_real(M, 1, 0, 4.0);
+    real_2x2_jacobi_svd(M, cl, sl, cr, sr, 1, 0);
+    applyOnTheLeft(M, 1, 0, cl, sl); applyOnTheRight(M, 1, 0, cr, sr);
+    std::printf("rot2x2 real=%d offdiag=%.3e %.3e cl=%.17g sl=%.17g cr=%.17g sr=%.17g\n", (int)real, M(1, 0), M(0, 1), cl, sl, cr, sr);
+    double cl2, sl2, cr2, sr2; Mat_m M2(2, 2); M2(0, 0) = 1; M2(0, 1) = 1e-12; M2(1, 0) = 0; M2(1, 1) = 2;
+    real_2x2_jacobi_svd_par(M2, cl2, sl2, cr2, sr2, 0, 1);
+    std::printf("rot2x2_par cr=%.17g sr=%.17g\n", cr2, sr2);
+    JacobiRotation r1(0.6, 0.8); Vec_v e(2); e(0) = 1; e(1) = 0; Vec_v re = r1.apply(e);
+    std::printf("rotation apply %.17g %.17g\n", re(0), re(1));
+  }
   JacobiRotation rot; bool okj = rot.makeJacobi(2.0, 0.5, 1.0);
   std::printf("makeJacobi ok=%d c=%.17g s=%.17g\n", (int)okj, rot.getC(), rot.getS());
   return 0;

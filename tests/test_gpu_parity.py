@@ -323,6 +323,17 @@ def test_cpp_dropin_headers(oracle, tmp_path):
     assert "QR class vs free function |dR|_1 = 0" in out
     assert abs(rd("pm", (1,))[0] - Sfull[0]) / Sfull[0] < 1e-9
     np.testing.assert_allclose(rd("AOmega", (m, l)), A @ Om, rtol=0, atol=1e-12 * np.linalg.norm(A @ Om))
+    # rotation helpers: the 2 x 2 block is diagonalised, and the numbers equal the oracle's restatement bit for bit
+    rot = dict(kv.split("=") for kv in out.split("rot2x2 ")[1].splitlines()[0].split() if "=" in kv)
+    offs = out.split("offdiag=")[1].split()[:2]
+    assert rot["real"] == "1" and abs(float(offs[0])) < 1e-15 and abs(float(offs[1])) < 1e-15
+    import ctypes as _ct
+    o = [_ct.c_double() for _ in range(4)]
+    oracle._lib().oc_real_2x2_jacobi_svd(_ct.c_double(3.0), _ct.c_double(1.0), _ct.c_double(0.5), _ct.c_double(4.0), _ct.c_double(np.finfo(float).tiny),
+                                         *[_ct.byref(x) for x in o])          # block (p=1, q=0): [m11 m10; m01 m00]
+    assert [float(rot[k]) for k in ("cl", "sl", "cr", "sr")] == [x.value for x in o]
+    assert "rot2x2_par cr=1 sr=0" in out                                      # the _par twin's 1e-10 floor (JacobiOperations.cpp:168)
+    assert "rotation apply 0.59999999999999998 -0.80000000000000004" in out   # [c s; -s c] * e1
     ok, c, s = True, *[float(x.split("=")[1]) for x in out.split("makeJacobi ")[1].split()[1:3]]
     lib = oracle._lib(); import ctypes
     cc = ctypes.c_double(); ss = ctypes.c_double()
