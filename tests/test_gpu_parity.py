@@ -419,3 +419,31 @@ def test_rsvd_csr_full_size_properties(engine):
     # s_i = ||Q^T A v_i|| <= ||A v_i||  (Q has orthonormal columns): every computed value is a lower bound
     AV = A @ V[:, :8]
     assert np.all(np.linalg.norm(AV, axis=0) >= S[:8] * (1 - 1e-12))
+
+
+def test_cpp_reference_test_driver(tmp_path):
+    """tests/cpp/rsvd_test_main.cpp = the reference's `make test` driver (tests/rSVD_test.cpp) against the drop-in headers,
+    run on the reference's five input matrices (regenerated); known answers from BASELINE.md section 3."""
+    import subprocess
+    from rsvd_kamaneh_raganato_terrana_b200 import mtx
+    root = Path(__file__).resolve().parent.parent
+    libdir = root / "rsvd_kamaneh_raganato_terrana_b200"
+    exe = tmp_path / "rsvd_test_main"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-I", str(root / "include"), "-o", str(exe), str(root / "tests" / "cpp" / "rsvd_test_main.cpp"),
+                    "-L", str(libdir), "-lrsvdb", f"-Wl,-rpath,{libdir}"], check=True)
+    (tmp_path / "input").mkdir()
+    for name, gen in W.C1_CASES:
+        A = gen()
+        mtx.save_coordinate(tmp_path / "input" / f"{name}.mtx", A, tol=0.0 if name == "sparse_matrix" else 1e-300)
+    out = subprocess.run([str(exe), str(tmp_path / "input"), str(tmp_path / "out")], check=True, capture_output=True, text=True).stdout
+    norms = {}
+    for block in out.split("Dataset: ")[1:]:
+        norms[block.split()[0]] = float(block.split("norm of diff : ")[1].split()[0])
+    assert set(norms) == {f"{n}.mtx" for n, _ in W.C1_CASES}
+    for n in (100, 110, 140, 160):
+        assert abs(norms[f"sparse_matrix{n}.mtx"] - np.sqrt(n - 16)) < 1e-4        # identity inputs: sqrt(n - 16); stdout has 6 digits, like the reference's
+    assert norms["sparse_matrix.mtx"] < 1e-7                                       # rank-2 ramp matrix
+    S = mtx.load_dense(tmp_path / "out" / "sparse_matrix_S.mtx").ravel()
+    assert abs(S[0] - 5.77391767e5) / 5.77391767e5 < 1e-8 and abs(S[1] - 1.44312761e3) / 1.44312761e3 < 1e-8
+    assert mtx.load_dense(tmp_path / "out" / "sparse_matrix100_U.mtx").shape == (100, 16)
+    assert mtx.load_dense(tmp_path / "out" / "sparse_matrix100_V.mtx").shape == (100, 16)
