@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdlib>
+#include <vector>
 
 namespace rsvdb {
 
@@ -954,6 +955,8 @@ k_node_gemm(const double* __restrict__ N, long long ldn, long long rows, int l, 
   }
 }
 
+#include "tsqr_cluster.cuh"
+
 // Fallback for panels wider than shared memory allows (l > 220 here): one CTA, unblocked Householder directly in global
 // memory (L2-resident for the sizes that reach it).  Same outputs as k_house_factor with a single leaf.
 __global__ void __launch_bounds__(1024, 1)
@@ -1063,6 +1066,10 @@ cudaError_t set_attr_blk_once() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_house_factor_la<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_node_factor_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_node_apply_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
   done = true;
   return cudaSuccess;
 }
@@ -1088,13 +1095,18 @@ cudaError_t Tsqr::plan(long long rows, int l) {
   size_t need = 0;
   long long r = rows;
   if (br_ == 0 || r <= 0) {           // single global-memory leaf
-    Level L; L.rows = r; L.nb = 1; L.off_R = need; need += (size_t)l * l; L.off_tau = need; need += (size_t)l; L.off_T = need; L.off_E = need;
+    Level L; L.rows = r; L.nb = 1; L.off_R = need; need += (size_t)l * l; L.off_tau = need; need += (size_t)l; L.off_T = need; L.off_E = need; L.cl = false; L.node_rows = 0;
     levels_.push_back(L);
     off_top_ = need; need += (size_t)l * l;
     off_scratch_ = need; need += (size_t)std::max<long long>(r, 1) * l;   // apply_global cannot run in place
   } else {
+    const bool use_cl = blk_ && !(dbg_mode() & 8) && cl_factor_smem(l) <= 227 * 1024 && cl_apply_smem(l) <= 227 * 1024;
     for (;;) {
-      Level L; L.rows = r; L.nb = (int)((r + br_ - 1) / br_);
+      Level L; L.rows = r;
+      // leaves: 256-row single-CTA blocks (all SMs busy); upper levels and mid-sized panels: 1024-row cluster nodes
+      L.cl = use_cl && r > 256 && (!levels_.empty() || r <= CL_ROWS);
+      L.node_rows = L.cl ? CL_ROWS : br_;
+      L.nb = (int)((r + L.node_rows - 1) / L.node_rows);
       L.off_R = need; need += (size_t)L.nb * l * l;
       L.off_tau = need; need += (size_t)L.nb * l;
       L.off_T = need; if (blk_) need += (size_t)L.nb * ((l + 7) / 8) * 64;
@@ -1125,7 +1137,9 @@ cudaError_t Tsqr::factor(cudaStream_t st, double* Y, long long ldy, int* launche
     cudaError_t e;
     if (blk_) {
       e = set_attr_blk_once(); if (e != cudaSuccess) return e;
-      if (dbg_mode() & 4)
+      if (L.cl)
+        k_node_factor_cl<<<L.nb * CL, BQ_THREADS, cl_factor_smem(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
+      else if (dbg_mode() & 4)
         k_house_factor_blk<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T, dbg_mode());
       else
         k_house_factor_la<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
@@ -1169,20 +1183,29 @@ cudaError_t Tsqr::form_q(cudaStream_t st, double* Y, long long ldy, const double
     auto level_V = [&](int i, double** V, long long* ldv) {
       if (i == 0) { *V = Y; *ldv = ldy; } else { *V = base + levels_[i - 1].off_R; *ldv = (long long)levels_[i - 1].nb * l_; }
     };
-    const double* Cleaf = Ctop; long long ldcleaf = ldc;
-    if (nlev > 1) {
-      if (nlev - 1 > 16) return cudaErrorInvalidValue;
-      // (A) explicit factor N_i = H [I; 0] of every upper level in ONE launch (in place over the reflectors)
+    // launch the levels listed in `which` (all of one kind) in one grid
+    auto launch_apply = [&](const std::vector<int>& which, bool cl, const double* C0, long long ldc0) -> cudaError_t {
+      if (which.empty()) return cudaSuccess;
+      if (which.size() > 16) return cudaErrorInvalidValue;
       ApplyTable tab; tab.n = 0; int first = 0;
-      for (int i = 1; i < nlev; ++i) {
+      for (int i : which) {
         double* V; long long ldv; level_V(i, &V, &ldv);
         ApplyLevel& a = tab.lv[tab.n++];
-        a.V = V; a.ldv = ldv; a.rows = levels_[i].rows; a.Tg = base + levels_[i].off_T; a.Ctop = nullptr; a.ldc = 0; a.Q = V; a.ldq = ldv;
-        a.first_block = first; first += levels_[i].nb;
+        a.V = V; a.ldv = ldv; a.rows = levels_[i].rows; a.Tg = base + levels_[i].off_T; a.Ctop = C0; a.ldc = ldc0; a.Q = V; a.ldq = ldv;
+        a.first_block = first; first += levels_[i].nb * (cl ? CL : 1);
       }
-      k_house_apply_blk<256><<<first, BQ_THREADS, smem, st>>>(tab, l_);
-      cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+      if (cl) k_node_apply_cl<<<first, BQ_THREADS, cl_apply_smem(l_), st>>>(tab, l_);
+      else k_house_apply_blk<256><<<first, BQ_THREADS, smem, st>>>(tab, l_);
       if (launches) ++*launches;
+      return cudaGetLastError();
+    };
+    const double* Cleaf = Ctop; long long ldcleaf = ldc;
+    if (nlev > 1) {
+      // (A) explicit factor N_i = H [I; 0] of every upper level (in place over the reflectors): one launch per node kind
+      std::vector<int> up_cl, up_sc;
+      for (int i = 1; i < nlev; ++i) (levels_[i].cl ? up_cl : up_sc).push_back(i);
+      cudaError_t e = launch_apply(up_cl, true, nullptr, 0); if (e != cudaSuccess) return e;
+      e = launch_apply(up_sc, false, nullptr, 0); if (e != cudaSuccess) return e;
       // (B) chain top-down: E_i[node b] = N_i[node b] * E_{i+1}[rows b*l .. (b+1)*l)   (E_top = N_top * Ctop)
       static bool ng_attr = false;
       const size_t ng_smem = ((size_t)l_ * l_ + (size_t)l_ * (NG_ROWS + 1)) * sizeof(double);
@@ -1192,7 +1215,8 @@ cudaError_t Tsqr::form_q(cudaStream_t st, double* Y, long long ldy, const double
         double* V; long long ldv; level_V(i, &V, &ldv);
         if (Epar) {
           double* E = base + levels_[i].off_E;
-          k_node_gemm<<<levels_[i].nb * (256 / NG_ROWS), 256, ng_smem, st>>>(V, ldv, levels_[i].rows, l_, 256, Epar, ldpar, E, levels_[i].rows);
+          const int nr = levels_[i].node_rows;
+          k_node_gemm<<<levels_[i].nb * (nr / NG_ROWS), 256, ng_smem, st>>>(V, ldv, levels_[i].rows, l_, nr, Epar, ldpar, E, levels_[i].rows);
           e = cudaGetLastError(); if (e != cudaSuccess) return e;
           if (launches) ++*launches;
           Epar = E; ldpar = levels_[i].rows;
@@ -1200,14 +1224,8 @@ cudaError_t Tsqr::form_q(cudaStream_t st, double* Y, long long ldy, const double
       }
       Cleaf = Epar; ldcleaf = ldpar;
     }
-    // (C) leaves
-    ApplyTable tab; tab.n = 1;
-    tab.lv[0].V = Y; tab.lv[0].ldv = ldy; tab.lv[0].rows = levels_[0].rows; tab.lv[0].Tg = base + levels_[0].off_T;
-    tab.lv[0].Ctop = Cleaf; tab.lv[0].ldc = ldcleaf; tab.lv[0].Q = Y; tab.lv[0].ldq = ldy; tab.lv[0].first_block = 0;
-    k_house_apply_blk<256><<<levels_[0].nb, BQ_THREADS, smem, st>>>(tab, l_);
-    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
-    if (launches) ++*launches;
-    return cudaSuccess;
+    // (C) level 0
+    return launch_apply(std::vector<int>{0}, levels_[0].cl, Cleaf, ldcleaf);
   }
   for (int i = (int)levels_.size() - 1; i >= 0; --i) {
     Level& L = levels_[i];

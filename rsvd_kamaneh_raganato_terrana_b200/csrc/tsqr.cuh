@@ -22,7 +22,7 @@ class Tsqr {
   int depth() const { return (int)levels_.size(); }
 
  private:
-  struct Level { long long rows; int nb; size_t off_R; size_t off_tau; size_t off_T; size_t off_E; };
+  struct Level { long long rows; int nb; size_t off_R; size_t off_tau; size_t off_T; size_t off_E; bool cl; int node_rows; };
   GemmWorkspace* ws_;
   std::vector<Level> levels_;
   long long rows_ = 0;
