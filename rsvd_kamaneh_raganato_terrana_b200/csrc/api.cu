@@ -102,7 +102,7 @@ int rsvdb_destroy(rsvdb_ctx* c) {
   comm_destroy(c);
   for (auto& s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (auto e : c->event_pool) cudaEventDestroy(e);
-  c->gemm_ws.release(); c->qr_ws.release(); c->qr2_ws.release(); c->tmp_ws.release(); c->svd_ws.release(); c->io_ws.release();
+  c->gemm_ws.release(); c->qr_ws.release(); c->qr2_ws.release(); c->tmp_ws.release(); c->svd_ws.release(); c->io_ws.release(); c->wide_ws.release();
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return RSVDB_OK;

@@ -19,6 +19,7 @@ struct rsvdb_ctx {
   rsvdb::GemmWorkspace tmp_ws;      // pipeline intermediates (Q, Z, B^T, small factors)
   rsvdb::GemmWorkspace svd_ws;      // small-SVD scratch
   rsvdb::GemmWorkspace io_ws;       // device copies for the *_host entry points
+  rsvdb::GemmWorkspace wide_ws;     // wide-panel QR (l > 100): R, projection coefficients, product buffer
   int64_t launches = 0;
   std::string err;
   // multi-GPU (row-sharded A); comm is an ncclComm_t resolved at run time (comm.cu)

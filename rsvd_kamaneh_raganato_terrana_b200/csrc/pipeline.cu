@@ -63,7 +63,83 @@ int copy2d(rsvdb_ctx* c, const double* src, int64_t lds, double* dst, int64_t ld
   return 0;
 }
 
+namespace {
+constexpr int QR_FAST_MAX = 100;    // widest panel the blocked / cluster TSQR holds in shared memory
+constexpr int QR_WIDE_BLOCK = 96;
+
+// Y (rows x cols, ldy) -= P (rows x cols, ldp)
+__global__ void k_sub(double* __restrict__ Y, long long ldy, const double* __restrict__ P, long long ldp, long long rows, int cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) for (int k = blockIdx.y; k < cols; k += gridDim.y) Y[(size_t)k * ldy + i] -= P[(size_t)k * ldp + i];
+}
+// R[r0 + i, c0 + j] (+)= W[i, j]
+__global__ void k_place(double* __restrict__ R, int ldr, int r0, int c0, const double* __restrict__ Wm, int ldw, int rows, int cols, int accumulate) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < rows * cols) {
+    const int i = e % rows, j = e / rows;
+    double* dst = R + (size_t)(c0 + j) * ldr + r0 + i;
+    *dst = accumulate ? *dst + Wm[(size_t)j * ldw + i] : Wm[(size_t)j * ldw + i];
+  }
+}
+}  // namespace
+
+// Panels wider than the shared-memory TSQR (l > 100): block Gram-Schmidt between column blocks of <= 96, Householder TSQR
+// inside each block.  Block k is projected twice against the finished blocks ("twice is enough"), factored, projected
+// once more and factored again, so that Q stays orthonormal to working precision even when a block is numerically
+// dependent on its predecessors (rank-deficient sketches); R is assembled from the projection coefficients.
+// All products run on the DMMA GEMM kernels; with row shards the coefficients are all-reduced.
+static int qr_wide(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bool sharded, const double** Rout) {
+  const int nblk = (l + QR_WIDE_BLOCK - 1) / QR_WIDE_BLOCK;
+  const int bw = (((l + nblk - 1) / nblk) + 7) & ~7;
+  const size_t d_R = (size_t)l * l, d_W = (size_t)l * bw, d_P = (size_t)std::max<int64_t>(rows, 1) * bw, d_s = (size_t)bw * bw;
+  RSVDB_CUDA(c, c->wide_ws.reserve((d_R + 2 * d_W + d_P + 3 * d_s + 64) * sizeof(double)));
+  double* R = c->wide_ws.ptr; double* Wb = R + d_R; double* W2 = Wb + d_W; double* P = W2 + d_W;
+  double* R1 = P + d_P; double* R2 = R1 + d_s; double* R21 = R2 + d_s;
+  cudaStream_t st = c->stream;
+  RSVDB_CUDA(c, cudaMemsetAsync(R, 0, d_R * sizeof(double), st));
+  const bool dist = sharded && c->nranks > 1;
+  int nl = 0;
+  auto project = [&](double* Yk, int col0, int ck, double* Wout) -> int {       // Wout = Qp^T Yk ; Yk -= Qp Wout
+    RSVDB_CUDA(c, gemm_at(c->gemm_ws, st, c->nsm, Y, rows, col0, ldy, Yk, ldy, ck, Wout, col0, 0, &nl));
+    if (dist) RSVDB_TRY(comm_allreduce_sum(c, Wout, (size_t)col0 * ck));
+    RSVDB_CUDA(c, gemm_an(c->gemm_ws, st, c->nsm, Y, rows, col0, ldy, Wout, col0, ck, P, rows, &nl));
+    if (rows > 0) { dim3 g((unsigned)((rows + 255) / 256), (unsigned)std::min(ck, 64)); k_sub<<<g, 256, 0, st>>>(Yk, ldy, P, rows, rows, ck); ++nl; }
+    return 0;
+  };
+  for (int col0 = 0; col0 < l; col0 += bw) {
+    const int ck = std::min(bw, l - col0);
+    double* Yk = Y + (size_t)col0 * ldy;
+    const double* Rk = nullptr;
+    if (col0 == 0) {
+      RSVDB_TRY(qr_inplace(c, Yk, rows, ck, ldy, sharded, &Rk));
+      k_place<<<(ck * ck + 255) / 256, 256, 0, st>>>(R, l, 0, 0, Rk, ck, ck, ck, 0); ++nl;
+      continue;
+    }
+    // Y_k = Qp (W_a + W_b) + Y_k''            (two projections)
+    RSVDB_TRY(project(Yk, col0, ck, Wb));
+    k_place<<<(col0 * ck + 255) / 256, 256, 0, st>>>(R, l, 0, col0, Wb, col0, col0, ck, 0); ++nl;
+    RSVDB_TRY(project(Yk, col0, ck, Wb));
+    k_place<<<(col0 * ck + 255) / 256, 256, 0, st>>>(R, l, 0, col0, Wb, col0, col0, ck, 1); ++nl;
+    // Y_k'' = Q1 R1
+    RSVDB_TRY(qr_inplace(c, Yk, rows, ck, ldy, sharded, &Rk));
+    RSVDB_CUDA(c, cudaMemcpyAsync(R1, Rk, (size_t)ck * ck * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // Q1 = Qp W_c + Q2 R2                     (re-orthogonalise the block against its predecessors)
+    RSVDB_TRY(project(Yk, col0, ck, W2));
+    RSVDB_TRY(qr_inplace(c, Yk, rows, ck, ldy, sharded, &Rk));
+    RSVDB_CUDA(c, cudaMemcpyAsync(R2, Rk, (size_t)ck * ck * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // R[0:col0, blk] += W_c R1 ;  R[blk, blk] = R2 R1
+    RSVDB_CUDA(c, gemm_generic(st, 0, 0, col0, ck, ck, 1.0, W2, col0, R1, ck, 1.0, R + (size_t)col0 * l, l)); ++nl;
+    RSVDB_CUDA(c, gemm_generic(st, 0, 0, ck, ck, ck, 1.0, R2, ck, R1, ck, 0.0, R21, ck)); ++nl;
+    k_place<<<(ck * ck + 255) / 256, 256, 0, st>>>(R, l, col0, col0, R21, ck, ck, ck, 0); ++nl;
+  }
+  RSVDB_CUDA(c, cudaGetLastError());
+  c->launches += nl;
+  if (Rout) *Rout = R;
+  return 0;
+}
+
 int qr_inplace(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bool sharded, const double** R) {
+  if (l > QR_FAST_MAX && rows >= 4 * (int64_t)l) return qr_wide(c, Y, rows, l, ldy, sharded, R);
   PhaseTimer pt(c, PH_QR);
   int k = 0;
   Tsqr t(&c->qr_ws);

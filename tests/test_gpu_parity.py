@@ -107,6 +107,9 @@ def test_device_generated_omega_is_seeded_and_normal(engine):
     ("l_equals_n_300x60", lambda: np.random.default_rng(3).standard_normal((300, 60)), 60),
     ("l128_3000x500", lambda: np.random.default_rng(4).standard_normal((3000, 500)), 128),
     ("l150_wide_panel_2000x400", lambda: np.random.default_rng(6).standard_normal((2000, 400)), 150),
+    ("l128_wide_panel_tall_20000x700", lambda: np.random.default_rng(7).standard_normal((20000, 60)) @ np.random.default_rng(8).standard_normal((60, 700))
+     + 1e-4 * np.random.default_rng(9).standard_normal((20000, 700)), 128),
+    ("l200_rank_deficient_pod_8000x900", lambda: W.c4_pod(8000, 900), 200),
 ])
 def test_configs_vs_oracle(engine, oracle, name, gen, l):
     A = gen()
