@@ -1053,6 +1053,7 @@ int pick_br(int l) {
   return 0;
 }
 
+int cl_max_nodes() { static int m = -1; if (m < 0) { const char* e = getenv("RSVDB_TSQR_CL_MAX"); m = e ? atoi(e) : 99; } return m; }
 int dbg_mode() { static int m = -1; if (m < 0) { const char* e = getenv("RSVDB_TSQR_DEBUG"); m = e ? atoi(e) : 0; } return m; }   // timing experiments only
 
 size_t blk_smem_bytes(int l) { return ((size_t)(l + 8) * (256 + 4) + 64 + 720 + (size_t)l) * sizeof(double); }
@@ -1104,7 +1105,10 @@ cudaError_t Tsqr::plan(long long rows, int l) {
     for (;;) {
       Level L; L.rows = r;
       // leaves: 256-row single-CTA blocks (all SMs busy); upper levels and mid-sized panels: 1024-row cluster nodes
-      L.cl = use_cl && r > 256 && (!levels_.empty() || r <= CL_ROWS);
+      // cluster nodes pay off when the level is latency-bound (few nodes); a level with hundreds of nodes is
+      // throughput-bound and runs better as independent 256-row blocks
+      const long long nb_cl = (r + CL_ROWS - 1) / CL_ROWS;
+      L.cl = use_cl && r > 256 && nb_cl <= cl_max_nodes() && (!levels_.empty() || r <= CL_ROWS);
       L.node_rows = L.cl ? CL_ROWS : br_;
       L.nb = (int)((r + L.node_rows - 1) / L.node_rows);
       L.off_R = need; need += (size_t)L.nb * l * l;
