@@ -450,3 +450,30 @@ def test_cpp_reference_test_driver(tmp_path):
     assert abs(S[0] - 5.77391767e5) / 5.77391767e5 < 1e-8 and abs(S[1] - 1.44312761e3) / 1.44312761e3 < 1e-8
     assert mtx.load_dense(tmp_path / "out" / "sparse_matrix100_U.mtx").shape == (100, 16)
     assert mtx.load_dense(tmp_path / "out" / "sparse_matrix100_V.mtx").shape == (100, 16)
+
+
+def test_cpp_older_api_headers(oracle, tmp_path):
+    """the older 5-argument rSVD / singularValueDecomposition / powerMethod API
+    (image_compression/include/{rSVD,SVD,PowerMethod}.hpp) routed onto the same kernels."""
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    libdir = root / "rsvd_kamaneh_raganato_terrana_b200"
+    exe = tmp_path / "rsvd_v1_test"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-I", str(root / "include"), "-o", str(exe), str(root / "tests" / "cpp" / "rsvd_v1_test.cpp"),
+                    "-L", str(libdir), "-lrsvdb", f"-Wl,-rpath,{libdir}"], check=True)
+    m, n, l = 120, 90, 15                      # image_compression/tests/rSVD_test1.cpp: k = 5, p = 10
+    rng = np.random.default_rng(5)
+    A = np.asfortranarray(rng.standard_normal((m, 12)) @ np.diag(0.5 ** np.arange(12)) @ rng.standard_normal((12, n)))
+    A.ravel(order="F").tofile(tmp_path / "A.bin")
+    out = subprocess.run([str(exe), str(tmp_path / "A.bin"), str(m), str(n), str(l), str(tmp_path / "o")], check=True, capture_output=True, text=True).stdout
+    assert "rSVD(5 args): U 120 x 15, S 15, V 90 x 15" in out and "SVD dim=4: V 90 x 4" in out
+    rd = lambda name, shape: np.fromfile(tmp_path / f"o_{name}.bin").reshape(shape, order="F")
+    U, S, V = rd("U", (m, l)), rd("S", (l,)), rd("V", (n, l))
+    Sfull = np.linalg.svd(A, compute_uv=False)
+    assert np.max(np.abs(S[:8] - Sfull[:8]) / Sfull[:8]) < 1e-6                       # rank-12 input, q = 1, power back-end
+    assert np.linalg.norm(A - (U[:, :12] * S[:12]) @ V[:, :12].T) <= 1e-6 * np.linalg.norm(A)
+    s2, U2, V2, A2 = rd("s2", (4,)), rd("U2", (m, 4)), rd("V2", (n, 4)), rd("A2", (m, n))
+    assert np.max(np.abs(s2 - Sfull[:4]) / Sfull[:4]) < 1e-8
+    np.testing.assert_allclose(A2, A - (U2 * s2) @ V2.T, atol=1e-12 * np.linalg.norm(A))    # A deflated in place
+    assert np.linalg.norm(A2, 2) <= Sfull[4] * (1 + 1e-6)
+    assert abs(rd("pm", (1,))[0] - Sfull[0]) / Sfull[0] < 1e-9
