@@ -14,7 +14,7 @@ def test_library_exports_every_declared_symbol():
     from rsvd_kamaneh_raganato_terrana_b200 import capi
     lib = capi.load()
     declared = capi.exported_symbols()
-    assert len(declared) >= 29
+    assert len(declared) >= 32
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/rsvdb.h but not exported"
     out = subprocess.run(["nm", "-D", "--defined-only", str(capi.LIB_PATH)], capture_output=True, text=True, check=True).stdout
@@ -47,7 +47,7 @@ def test_no_cpu_fallback():
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing in the product package may import, load or link it."""
     pkg = ROOT / "rsvd_kamaneh_raganato_terrana_b200"
-    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list((ROOT / "include").glob("*")):
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + [q for q in (ROOT / "include").rglob("*") if q.is_file()]:
         text = p.read_text()
         for pat in (r"^\s*(from|import)\s+oracle", r"rsvd_oracle", r"liboracle", r"libref_rsvd", r"oracle/", r"oracle_c"):
             assert not re.search(pat, text, flags=re.M), f"{p} reaches into the oracle ({pat})"
