@@ -91,6 +91,8 @@ int rsvdb_create(rsvdb_ctx** out, int device) {
   c->nsm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RSVDB_ERR_CUDA; }
   c->stream = c->own_stream;
+  if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RSVDB_ERR_CUDA; }
+  for (auto& e : c->side_ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete c; return RSVDB_ERR_CUDA; }
   *out = c;
   return RSVDB_OK;
 }
@@ -100,6 +102,8 @@ int rsvdb_destroy(rsvdb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   comm_destroy(c);
+  if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
+  for (auto e : c->side_ev) if (e) cudaEventDestroy(e);
   for (auto& s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (auto e : c->event_pool) cudaEventDestroy(e);
   c->gemm_ws.release(); c->qr_ws.release(); c->qr2_ws.release(); c->tmp_ws.release(); c->svd_ws.release(); c->io_ws.release(); c->wide_ws.release();

@@ -13,6 +13,8 @@ struct rsvdb_ctx {
   int nsm = 148;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;   // overlaps the explicit-factor formation of upper TSQR levels with the factor chain
+  cudaEvent_t side_ev[20] = {};          // [0..15] per tree level, [16] "side work done"
   rsvdb::GemmWorkspace gemm_ws;     // split-K partial tiles
   rsvdb::GemmWorkspace qr_ws;       // TSQR tree of the local panel
   rsvdb::GemmWorkspace qr2_ws;      // TSQR tree of the all-gathered R stack (multi-GPU)

@@ -142,7 +142,7 @@ int qr_inplace(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bool s
   if (l > QR_FAST_MAX && rows >= 4 * (int64_t)l) return qr_wide(c, Y, rows, l, ldy, sharded, R);
   PhaseTimer pt(c, PH_QR);
   int k = 0;
-  Tsqr t(&c->qr_ws);
+  Tsqr t(&c->qr_ws, c->side_stream, c->side_ev);
   RSVDB_CUDA(c, t.plan(rows, l));
   RSVDB_CUDA(c, t.factor(c->stream, Y, ldy, &k));
   const bool dist = sharded && c->nranks > 1;

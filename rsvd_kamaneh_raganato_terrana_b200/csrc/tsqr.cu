@@ -1127,6 +1127,7 @@ cudaError_t Tsqr::plan(long long rows, int l) {
 
 cudaError_t Tsqr::factor(cudaStream_t st, double* Y, long long ldy, int* launches) {
   double* base = ws_->ptr;
+  upper_done_ = false;
   if (br_ == 0) {
     Level& L = levels_[0];
     k_house_factor_global<<<1, 1024, 0, st>>>(Y, ldy, L.rows, l_, base + L.off_tau, base + L.off_R, l_);
@@ -1158,8 +1159,23 @@ cudaError_t Tsqr::factor(cudaStream_t st, double* Y, long long ldy, int* launche
     }
     e = cudaGetLastError(); if (e != cudaSuccess) return e;
     if (launches) ++*launches;
+    if (blk_ && i >= 1 && side_ && ev_ && i < 16) {
+      // level i is factored: form its explicit factor N_i = H [I; 0] (in place over the reflectors) on the side stream
+      // while the next level is being factored on the main stream
+      e = cudaEventRecord(ev_[i], st); if (e != cudaSuccess) return e;
+      e = cudaStreamWaitEvent(side_, ev_[i], 0); if (e != cudaSuccess) return e;
+      ApplyTable tab; tab.n = 1;
+      tab.lv[0].V = cur; tab.lv[0].ldv = ld; tab.lv[0].rows = L.rows; tab.lv[0].Tg = base + L.off_T; tab.lv[0].Ctop = nullptr; tab.lv[0].ldc = 0;
+      tab.lv[0].Q = cur; tab.lv[0].ldq = ld; tab.lv[0].first_block = 0;
+      if (L.cl) k_node_apply_cl<<<L.nb * CL, BQ_THREADS, cl_apply_smem(l_), side_>>>(tab, l_);
+      else k_house_apply_blk<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), side_>>>(tab, l_);
+      e = cudaGetLastError(); if (e != cudaSuccess) return e;
+      if (launches) ++*launches;
+      upper_done_ = true;
+    }
     cur = base + L.off_R; ld = ldr;
   }
+  if (upper_done_) { cudaError_t e = cudaEventRecord(ev_[16], side_); if (e != cudaSuccess) return e; }
   return cudaSuccess;
 }
 
@@ -1208,8 +1224,12 @@ cudaError_t Tsqr::form_q(cudaStream_t st, double* Y, long long ldy, const double
       // (A) explicit factor N_i = H [I; 0] of every upper level (in place over the reflectors): one launch per node kind
       std::vector<int> up_cl, up_sc;
       for (int i = 1; i < nlev; ++i) (levels_[i].cl ? up_cl : up_sc).push_back(i);
-      cudaError_t e = launch_apply(up_cl, true, nullptr, 0); if (e != cudaSuccess) return e;
-      e = launch_apply(up_sc, false, nullptr, 0); if (e != cudaSuccess) return e;
+      cudaError_t e = cudaSuccess;
+      if (upper_done_) { e = cudaStreamWaitEvent(st, ev_[16], 0); if (e != cudaSuccess) return e; }   // formed on the side stream during factor()
+      else {
+        e = launch_apply(up_cl, true, nullptr, 0); if (e != cudaSuccess) return e;
+        e = launch_apply(up_sc, false, nullptr, 0); if (e != cudaSuccess) return e;
+      }
       // (B) chain top-down: E_i[node b] = N_i[node b] * E_{i+1}[rows b*l .. (b+1)*l)   (E_top = N_top * Ctop)
       static bool ng_attr = false;
       const size_t ng_smem = ((size_t)l_ * l_ + (size_t)l_ * (NG_ROWS + 1)) * sizeof(double);

@@ -8,7 +8,7 @@ namespace rsvdb {
 
 class Tsqr {
  public:
-  explicit Tsqr(GemmWorkspace* ws) : ws_(ws) {}
+  explicit Tsqr(GemmWorkspace* ws, cudaStream_t side = nullptr, cudaEvent_t* events = nullptr) : ws_(ws), side_(side), ev_(events) {}
   // Size the tree for a rows x l panel and reserve workspace.
   cudaError_t plan(long long rows, int l);
   // Factor Y in place (reflectors overwrite Y).  Afterwards R_local() is the l x l upper-triangular factor of this panel.
@@ -24,6 +24,9 @@ class Tsqr {
  private:
   struct Level { long long rows; int nb; size_t off_R; size_t off_tau; size_t off_T; size_t off_E; bool cl; int node_rows; };
   GemmWorkspace* ws_;
+  cudaStream_t side_ = nullptr;        // optional: upper-level explicit factors are formed here, overlapping the factor chain
+  cudaEvent_t* ev_ = nullptr;          // >= 17 events
+  bool upper_done_ = false;
   std::vector<Level> levels_;
   long long rows_ = 0;
   int l_ = 0, br_ = 0;
