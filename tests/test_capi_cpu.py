@@ -51,3 +51,18 @@ def test_product_never_imports_oracle():
         text = p.read_text()
         for pat in (r"^\s*(from|import)\s+oracle", r"rsvd_oracle", r"liboracle", r"libref_rsvd", r"oracle/", r"oracle_c"):
             assert not re.search(pat, text, flags=re.M), f"{p} reaches into the oracle ({pat})"
+
+
+def test_cpp_dropin_headers_compile_and_link():
+    """The C++ drop-in headers (the reference's file names and symbols) compile with a plain host compiler and link against
+    librsvdb.so -- no CUDA headers, no torch, no Eigen needed by a caller."""
+    libdir = ROOT / "rsvd_kamaneh_raganato_terrana_b200"
+    out = ROOT / "build"
+    out.mkdir(exist_ok=True)
+    for src in ("rsvd_dropin_test.cpp", "rsvd_test_main.cpp", "rsvd_v1_test.cpp"):
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-o", str(out / (src[:-4] + "_cpu")),
+                        str(ROOT / "tests" / "cpp" / src), "-L", str(libdir), "-lrsvdb", f"-Wl,-rpath,{libdir}"], check=True)
+    # every reference header name on the path has a drop-in of the same name
+    for h in ("rSVD.hpp", "SVD_class.hpp", "QR.hpp", "PM.hpp", "Jacobi_Class.hpp", "JacobiOperations.hpp", "matrixOperations.hpp",
+              "image_compression/rSVD.hpp", "image_compression/SVD.hpp", "image_compression/PowerMethod.hpp", "image_compression/QR.hpp"):
+        assert (ROOT / "include" / h).exists(), h
