@@ -12,6 +12,7 @@
 #include "jacobi.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace rsvdb {
 
@@ -139,12 +140,199 @@ k_jacobi(const double* __restrict__ W, long long ldw, int k, int transpose_in, d
   if (tid == 0 && info) { info[0] = converged ? sweep : -sweep; info[1] = s_total; }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Cluster variant: the single-CTA kernel above is bound by shared-memory bandwidth (every round-robin step reads and
+// writes all of X and Z through one SM: 4 * k^2 * 8 bytes).  Here the ROWS of X and Z are split over a cluster of
+// JC = 4 CTAs, so each SM moves a quarter of the bytes; per step and pair only the three partial inner products cross the
+// cluster (remote st.shared::cluster of 3 doubles to each peer + one hardware cluster barrier).  Every CTA sums the
+// partials in rank order and therefore takes bit-identical rotation decisions, which keeps the loops (and barriers) of
+// the four CTAs in lock step without any further communication.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int JC = 4;
+
+__device__ __forceinline__ unsigned jc_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void jc_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void jc_store(double* p, unsigned rank, double v) {
+  unsigned la = static_cast<unsigned>(__cvta_generic_to_shared(p)), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+
+// RPL: rows of the CTA's slice per lane of a 16-lane group (slice rows sr = ceil(k / JC) <= 16 * RPL).
+template <int RPL>
+__global__ void __cluster_dims__(JC, 1, 1) __launch_bounds__(1024, 1)
+k_jacobi_cl(const double* __restrict__ W, long long ldw, int k, int transpose_in, double* __restrict__ Uo, long long ldu,
+            double* __restrict__ So, double* __restrict__ Zo, long long ldz, int max_sweeps, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  __shared__ int s_rot;
+  __shared__ int s_total;
+  const unsigned rank = jc_rank();
+  const int sr = (k + JC - 1) / JC;                 // slice rows
+  const int r0 = (int)rank * sr;
+  const int nr = max(0, min(sr, k - r0));
+  const int n = (k + 1) & ~1, npairs = n >> 1;
+  double* X = sm;                                   // k columns of sr rows
+  double* Z = X + (size_t)k * sr;
+  double* xch = Z + (size_t)k * sr;                 // [2][npairs][JC][4]
+  double* sig = xch + 2 * (size_t)npairs * JC * 4;  // [k][JC] partial squared norms, then [k] totals behind it
+  const int tid = threadIdx.x, hl = tid & 15, grp = tid >> 4, ngrp = blockDim.x >> 4;
+
+  for (int e = tid; e < k * sr; e += blockDim.x) {
+    const int i = e % sr, j = e / sr, gi = r0 + i;
+    double x = 0.0;
+    if (i < nr) x = transpose_in ? W[(size_t)gi * ldw + j] : W[(size_t)j * ldw + gi];
+    X[e] = x;
+    Z[e] = (i < nr && gi == j) ? 1.0 : 0.0;
+  }
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+
+  const double tol = sqrt((double)k) * (0.5 * DBL_EPSILON);
+  const double tol2 = tol * tol;
+  const int rounds = (npairs + ngrp - 1) / ngrp;
+  int sweep = 0, buf = 0; bool converged = (k < 2);
+  while (!converged && sweep < max_sweeps) {
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    for (int step = 0; step < n - 1; ++step) {
+      // (1) partial inner products of every pair over this CTA's rows -> all CTAs
+      for (int rd = 0; rd < rounds; ++rd) {
+        const int pi = grp + rd * ngrp;
+        int p = 0, q = k;
+        if (pi < npairs) {
+          if (pi == 0) { p = n - 1; q = step; }
+          else { p = (step + pi) % (n - 1); q = (step - pi + (n - 1)) % (n - 1); }
+          if (p > q) { const int t = p; p = q; q = t; }
+        }
+        const bool live = q < k;
+        const double* xp = X + (size_t)(live ? p : 0) * sr; const double* xq = X + (size_t)(live ? q : 0) * sr;
+        double a = 0.0, b = 0.0, g = 0.0;
+#pragma unroll
+        for (int ii = 0; ii < RPL; ++ii) {
+          const int i = hl + 16 * ii;
+          const bool on = live && i < nr;
+          const double vp = on ? xp[i] : 0.0, vq = on ? xq[i] : 0.0;
+          a = fma(vp, vp, a); b = fma(vq, vq, b); g = fma(vp, vq, g);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); g += __shfl_xor_sync(0xffffffffu, g, o);
+        }
+        if (pi < npairs && hl < 3 * JC) {             // lanes 0..11: value hl % 3 to CTA hl / 3
+          const double v = (hl % 3 == 0) ? a : ((hl % 3 == 1) ? b : g);
+          jc_store(xch + (((size_t)buf * npairs + pi) * JC + rank) * 4 + (hl % 3), (unsigned)(hl / 3), v);
+        }
+      }
+      jc_sync();
+      // (2) every CTA takes the same decision and rotates its rows
+      int nrot = 0;
+      for (int rd = 0; rd < rounds; ++rd) {
+        const int pi = grp + rd * ngrp;
+        if (pi >= npairs) continue;
+        int p, q;
+        if (pi == 0) { p = n - 1; q = step; }
+        else { p = (step + pi) % (n - 1); q = (step - pi + (n - 1)) % (n - 1); }
+        if (p > q) { const int t = p; p = q; q = t; }
+        if (q >= k) continue;
+        const double* xx = xch + ((size_t)buf * npairs + pi) * JC * 4;
+        double a = 0.0, b = 0.0, g = 0.0;
+#pragma unroll
+        for (int sR = 0; sR < JC; ++sR) { a += xx[sR * 4 + 0]; b += xx[sR * 4 + 1]; g += xx[sR * 4 + 2]; }
+        if (g * g > tol2 * (a * b) && fabs(g) > DBL_MIN) {
+          ++nrot;
+          const double d = b - a;
+          const double n2 = fma(d, d, 4.0 * g * g);
+          const double ir = rsqrt(n2);
+          const double c2 = fma(0.5 * fabs(d), ir, 0.5);
+          const double ic = rsqrt(c2);
+          const double c = c2 * ic;
+          const double s = ((d >= 0.0) ? g : -g) * ir * ic;
+          double* xp = X + (size_t)p * sr; double* xq = X + (size_t)q * sr;
+          double* zp = Z + (size_t)p * sr; double* zq = Z + (size_t)q * sr;
+#pragma unroll
+          for (int ii = 0; ii < RPL; ++ii) {
+            const int i = hl + 16 * ii;
+            if (i < nr) {
+              const double x1 = xp[i], x2 = xq[i];
+              xp[i] = c * x1 - s * x2; xq[i] = s * x1 + c * x2;
+              const double z1 = zp[i], z2 = zq[i];
+              zp[i] = c * z1 - s * z2; zq[i] = s * z1 + c * z2;
+            }
+          }
+        }
+      }
+      if (nrot && hl == 0) atomicAdd(&s_rot, nrot);
+      __syncthreads();
+      buf ^= 1;
+    }
+    ++sweep;
+    converged = (s_rot == 0);                       // identical on every CTA: same sums, same decisions
+    if (tid == 0) s_total += s_rot;
+    __syncthreads();
+  }
+
+  // singular values: column norms summed over the cluster
+  double* part = sig;                               // [k][JC]
+  double* tot = sig + (size_t)k * JC;               // [k]
+  for (int j = grp; j < k; j += ngrp) {
+    double a = 0.0;
+    for (int i = hl; i < nr; i += 16) a = fma(X[(size_t)j * sr + i], X[(size_t)j * sr + i], a);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (hl < JC) jc_store(part + (size_t)j * JC + rank, (unsigned)hl, a);
+  }
+  jc_sync();
+  for (int j = tid; j < k; j += blockDim.x) {
+    double a = 0.0;
+#pragma unroll
+    for (int sR = 0; sR < JC; ++sR) a += part[(size_t)j * JC + sR];
+    tot[j] = sqrt(a);
+  }
+  __syncthreads();
+  for (int j = grp; j < k; j += ngrp) {
+    const double sj = tot[j];
+    int r = 0;
+    for (int i = hl; i < k; i += 16) { const double si = tot[i]; r += (si > sj || (si == sj && i < j)) ? 1 : 0; }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    const double inv = (sj > 0.0) ? 1.0 / sj : 0.0;
+    if (rank == 0 && hl == 0) So[r] = sj;
+    for (int i = hl; i < nr; i += 16) {
+      const int gi = r0 + i;
+      Uo[(size_t)r * ldu + gi] = (sj > 0.0) ? X[(size_t)j * sr + i] * inv : (gi == j ? 1.0 : 0.0);
+      Zo[(size_t)r * ldz + gi] = Z[(size_t)j * sr + i];
+    }
+  }
+  if (rank == 0 && tid == 0 && info) { info[0] = converged ? sweep : -sweep; info[1] = s_total; }
+  jc_sync();                                        // peers may still be reading this CTA's shared memory
+}
+
 }  // namespace
 
 cudaError_t jacobi_svd_square(GemmWorkspace& ws, cudaStream_t st, const double* W, long long ldw, int k, int transpose_in,
                               double* U, long long ldu, double* S, double* Z, long long ldz, int* d_info, int* launches) {
   if (k <= 0) return cudaSuccess;
   if (k > 16 * JMAX_RPL) return cudaErrorInvalidValue;
+  {
+    const int sr = (k + JC - 1) / JC, npairs = ((k + 1) & ~1) >> 1;
+    const size_t cl_smem = (2 * (size_t)k * sr + 2 * (size_t)npairs * JC * 4 + (size_t)k * JC + k) * sizeof(double);
+    static const bool cl_off = getenv("RSVDB_JACOBI_NO_CLUSTER") != nullptr;
+    // measured: the per-step cluster barrier outweighs the bandwidth gain below k ~ 80 (k = 50: 0.99 vs 0.88 ms, k = 100: 1.18 vs 1.40 ms)
+    if (!cl_off && k >= 80 && cl_smem <= 220 * 1024 && sr <= 64) {
+      const int rplc = (sr + 15) / 16;
+#define JCL(R)                                                                                                         \
+      { static bool attr = false;                                                                                      \
+        if (!attr) { cudaError_t e = cudaFuncSetAttribute(k_jacobi_cl<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
+                     if (e != cudaSuccess) return e; attr = true; }                                                    \
+        k_jacobi_cl<R><<<JC, 1024, cl_smem, st>>>(W, ldw, k, transpose_in, U, ldu, S, Z, ldz, 60, d_info); }
+      if (rplc <= 1) JCL(1) else if (rplc <= 2) JCL(2) else if (rplc <= 3) JCL(3) else JCL(4)
+#undef JCL
+      if (launches) ++*launches;
+      return cudaGetLastError();
+    }
+  }
   const size_t smem_need = (2 * (size_t)k * k + k) * sizeof(double);
   const int use_smem = smem_need <= 220 * 1024;
   double* Xg = nullptr; double* Zg = nullptr;
