@@ -481,6 +481,32 @@ __device__ __forceinline__ void panel_factor(double* S, double* Vp, double* Tsm,
   }
 }
 
+// Transposing warp reduction of 8 per-lane values: after three halving exchanges (xor 16, 8, 4) every lane owns ONE column,
+// two more butterfly steps finish the sum.  9 shuffles instead of 40; returns the total of column `col` (valid in all lanes,
+// lanes with (lane & 3) == 0 publish it).
+__device__ __forceinline__ double reduce8_transposed(const double (&p)[8], int lane, int* col) {
+  double q[4], r2[2], s;
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double send = u16 ? p[i] : p[i + 4], keep = u16 ? p[i + 4] : p[i];
+    q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double send = u8 ? q[i] : q[i + 2], keep = u8 ? q[i + 2] : q[i];
+    r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const double send = u4 ? r2[0] : r2[1], keep = u4 ? r2[1] : r2[0];
+    s = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  *col = (u16 ? 4 : 0) + (u8 ? 2 : 0) + (u4 ? 1 : 0);
+  return s;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Look-ahead factor kernel.  The 16 warps form two teams: the ROW team (warps 0-7, one 32-row slab each) updates the
 // NEXT panel's 8 columns with the current panel's reflectors (cooperatively: per-slab partial V^T C on the tensor
@@ -523,14 +549,9 @@ __device__ __forceinline__ void panel_factor_la(double* S, double* Vtop, double*
       double p[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) p[c] = (c >= r && i > d) ? a[r] * a[c] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) if (c >= r) p[c] += __shfl_xor_sync(0xffffffffu, p[c], o);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) if (c >= r) red[b * 64 + c * 8 + warp] = p[c];
+      {
+        int colr; const double tcol = reduce8_transposed(p, lane, &colr);
+        if ((lane & 3) == 0) red[b * 64 + colr * 8 + warp] = tcol;
       }
       if (i == d) {
 #pragma unroll

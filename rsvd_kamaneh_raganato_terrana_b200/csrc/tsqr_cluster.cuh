@@ -68,14 +68,9 @@ __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double*
         double p[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) p[c] = (c >= r && gi > d) ? a[r] * a[c] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) if (c >= r) p[c] += __shfl_xor_sync(0xffffffffu, p[c], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) red[c * 8 + warp] = (c >= r) ? p[c] : 0.0;
+        {
+          int colr; const double tcol = reduce8_transposed(p, lane, &colr);
+          if ((lane & 3) == 0) red[colr * 8 + warp] = tcol;
         }
         if (gi == d) {
 #pragma unroll
