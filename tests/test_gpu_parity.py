@@ -477,3 +477,47 @@ def test_cpp_older_api_headers(oracle, tmp_path):
     np.testing.assert_allclose(A2, A - (U2 * s2) @ V2.T, atol=1e-12 * np.linalg.norm(A))    # A deflated in place
     assert np.linalg.norm(A2, 2) <= Sfull[4] * (1 + 1e-6)
     assert abs(rd("pm", (1,))[0] - Sfull[0]) / Sfull[0] < 1e-9
+
+
+def test_device_entry_points_stay_inside_their_buffers(engine):
+    """compute-sanitizer is not available on this pool: outputs live between sentinel guard bands that must survive.
+    Covers the GEMMs (direct and split-K stores), TSQR (leaves, cluster nodes, wide panels) and the whole rSVD."""
+    import torch
+    dev = torch.device("cuda:0")
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    G = 4096                                               # guard doubles on each side
+    SENT = -7.25e300
+
+    def guarded(n_elems):
+        buf = torch.full((n_elems + 2 * G,), SENT, dtype=torch.float64, device=dev)
+        return buf, buf[G:G + n_elems]
+
+    def intact(buf, n_elems):
+        return bool((buf[:G] == SENT).all().item() and (buf[G + n_elems:] == SENT).all().item())
+
+    for (m, n, l) in [(1000, 300, 20), (5001 - 1, 777 + 1, 100), (4096, 4096, 50), (130, 50, 128), (25000, 1000, 104), (333, 130, 7)]:
+        A = torch.randn((n, m), dtype=torch.float64, device=dev); X = torch.randn((l, n), dtype=torch.float64, device=dev)
+        Q = torch.randn((l, m), dtype=torch.float64, device=dev)
+        by, Y = guarded(m * l); bz, Z = guarded(n * l); bb, B = guarded(n * l)
+        engine.gemm_an_dev(A.data_ptr(), m, n, m, X.data_ptr(), n, l, Y.data_ptr(), m)
+        engine.gemm_at_dev(A.data_ptr(), m, n, m, Q.data_ptr(), m, l, Z.data_ptr(), n, False)
+        engine.gemm_at_dev(A.data_ptr(), m, n, m, Q.data_ptr(), m, l, B.data_ptr(), l, True)
+        torch.cuda.synchronize()
+        assert intact(by, m * l) and intact(bz, n * l) and intact(bb, n * l), (m, n, l)
+        assert not bool((Y == SENT).any().item()) and not bool((Z == SENT).any().item()) and not bool((B == SENT).any().item())
+    for (rows, l) in [(256, 100), (1000, 100), (25000, 100), (777, 33), (3000, 64), (5000, 128), (20000, 16), (300, 110)]:
+        by, Y = guarded(rows * l); br, R = guarded(l * l)
+        Y.normal_()
+        engine.qr_dev(Y.data_ptr(), rows, l, rows, False, R.data_ptr())
+        torch.cuda.synchronize()
+        assert intact(by, rows * l) and intact(br, l * l), (rows, l)
+        Qm = Y.view(l, rows)
+        assert (Qm @ Qm.T - torch.eye(l, dtype=torch.float64, device=dev)).norm().item() < 1e-11
+    for (m, n, l) in [(3000, 400, 32), (20000, 1500, 100), (1200, 900, 120)]:
+        A = torch.randn((n, m), dtype=torch.float64, device=dev); Om = torch.randn((l, n), dtype=torch.float64, device=dev)
+        bu, U = guarded(m * l); bv, V = guarded(n * l); bs, S = guarded(l)
+        engine.rsvd_dev(A.data_ptr(), m, n, m, Om.data_ptr(), n, l, 1, SVDMethod.Jacobi, U.data_ptr(), m, S.data_ptr(), V.data_ptr(), n)
+        torch.cuda.synchronize()
+        assert intact(bu, m * l) and intact(bv, n * l) and intact(bs, l), (m, n, l)
+        assert bool(torch.isfinite(S).all().item()) and bool((S[:-1] >= S[1:]).all().item())
+    engine.lib.rsvdb_use_own_stream(engine.h)
