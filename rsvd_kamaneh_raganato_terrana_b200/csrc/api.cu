@@ -250,9 +250,9 @@ int rsvdb_intermediate_step_host(rsvdb_ctx* c, const double* A, int64_t m, int64
   RSVDB_CUDA(c, c->io_ws.reserve(need));
   IoArena ar(c);
   double* dA = ar.take((size_t)ldA * n); double* dO = ar.take((size_t)ldO * l); double* dQ = ar.take((size_t)ldA * l);
-  RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
   RSVDB_TRY(h2d(c, dO, ldO, Omega, ldo, n, l));
-  RSVDB_TRY(range_finder(c, dA, m, n, ldA, dO, ldO, l, q, dQ, ldA));
+  const HostUpload up{A, lda};
+  RSVDB_TRY(range_finder(c, dA, m, n, ldA, dO, ldO, l, q, dQ, ldA, &up));
   RSVDB_TRY(d2h(c, Q, ldq, dQ, ldA, m, l));
   RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RSVDB_OK;
@@ -273,10 +273,10 @@ int rsvdb_rsvd_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t
   IoArena ar(c);
   double* dA = ar.take((size_t)ldA * n); double* dO = ar.take((size_t)ldO * l); double* dU = ar.take((size_t)ldA * l);
   double* dV = ar.take((size_t)ldO * l); double* dS = ar.take((size_t)l);
-  RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
   if (Omega) { RSVDB_TRY(h2d(c, dO, ldO, Omega, ldo, n, l)); }
   else { RSVDB_TRY(rsvdb_generate_omega_dev(c, n, l, seed, dO, ldO)); }
-  RSVDB_TRY(rsvd_device(c, dA, m, n, ldA, dO, ldO, l, q, method, dU, ldA, dS, dV, ldO, seed));
+  const HostUpload up{A, lda};                          // A is uploaded block by block underneath the first product
+  RSVDB_TRY(rsvd_device(c, dA, m, n, ldA, dO, ldO, l, q, method, dU, ldA, dS, dV, ldO, seed, &up));
   RSVDB_TRY(d2h(c, U, ldu, dU, ldA, m, k));
   RSVDB_TRY(d2h(c, S, k, dS, k, k, 1));
   RSVDB_TRY(d2h(c, V, ldv, dV, ldO, n, k));

@@ -200,13 +200,43 @@ static int gemm_at_phase(rsvdb_ctx* c, const double* A, int64_t K, int64_t M, in
   return 0;
 }
 
+// First pass with A arriving over PCIe: row block i is copied on the side stream while block i-1 is multiplied.
+static int upload_and_first_pass(rsvdb_ctx* c, double* A, int64_t m, int64_t n, int64_t lda, const HostUpload& up,
+                                 const double* Omega, int64_t ldo, int l, double* Q, int64_t ldq) {
+  constexpr int kMaxBlocks = 16;                       // side_ev[0..15]
+  const size_t bytes = (size_t)m * n * sizeof(double);
+  int nb = (int)std::min<size_t>(kMaxBlocks, bytes >> 26);   // blocks of >= 64 MB, else the split costs more than it hides
+  if (nb < 2 || m < 512) nb = 1;
+  int64_t rows_b = ((m + nb - 1) / nb + 255) & ~int64_t(255);
+  RSVDB_CUDA(c, cudaEventRecord(c->side_ev[16], c->stream));           // the device buffer may still be read by earlier work
+  RSVDB_CUDA(c, cudaStreamWaitEvent(c->side_stream, c->side_ev[16], 0));
+  int b = 0;
+  for (int64_t r0 = 0; r0 < m; r0 += rows_b, ++b) {
+    const int64_t r = std::min(rows_b, m - r0);
+    if (r == m && lda == m && up.lda == m) {
+      RSVDB_CUDA(c, cudaMemcpyAsync(A, up.A, bytes, cudaMemcpyHostToDevice, c->side_stream));
+    } else {
+      RSVDB_CUDA(c, cudaMemcpy2DAsync(A + r0, (size_t)lda * 8, up.A + r0, (size_t)up.lda * 8, (size_t)r * 8, (size_t)n,
+                                      cudaMemcpyHostToDevice, c->side_stream));
+    }
+    RSVDB_CUDA(c, cudaEventRecord(c->side_ev[b], c->side_stream));
+    RSVDB_CUDA(c, cudaStreamWaitEvent(c->stream, c->side_ev[b], 0));
+    RSVDB_TRY(gemm_an_phase(c, A + r0, r, n, lda, Omega, ldo, l, Q + r0, ldq));
+  }
+  return 0;
+}
+
 int range_finder(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
-                 int l, int q, double* Q, int64_t ldq) {
+                 int l, int q, double* Q, int64_t ldq, const HostUpload* up) {
   if (l <= 0 || q < 0) return fail(c, -1, "range_finder: l must be positive and q non-negative");
   // Z (n x l) lives in tmp_ws at offset 0
   RSVDB_CUDA(c, c->tmp_ws.reserve(std::max<size_t>(c->tmp_ws.bytes, (size_t)n * l * sizeof(double))));
   double* Z = c->tmp_ws.ptr;
-  RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Omega, ldo, l, Q, ldq));            // Y = A * Omega          src/rSVD.cpp:59
+  if (up && up->A && m > 0) {
+    RSVDB_TRY(upload_and_first_pass(c, const_cast<double*>(A), m, n, lda, *up, Omega, ldo, l, Q, ldq));
+  } else {
+    RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Omega, ldo, l, Q, ldq));          // Y = A * Omega          src/rSVD.cpp:59
+  }
   RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));                       // Q = qr(Y).Q            :60-61
   for (int it = 0; it < q; ++it) {                                             // :62
     RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, ldq, l, Z, n, 0, true));       // Y = A^T * Q            :63
@@ -258,7 +288,8 @@ int small_svd_jacobi(rsvdb_ctx* c, const double* M, int64_t ldm, const double* M
 }
 
 int rsvd_device(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
-                int l, int q, int method, double* U, int64_t ldu, double* S, double* V, int64_t ldv, uint64_t seed) {
+                int l, int q, int method, double* U, int64_t ldu, double* S, double* V, int64_t ldv, uint64_t seed,
+                const HostUpload* up) {
   if (method != 0 && method != 1 && method != 2) return fail(c, -1, "Unsupported SVD method");   // src/rSVD.cpp:122-123
   if (l <= 0 || n <= 0 || m < 0) return fail(c, -1, "rSVD: bad shape");
   const int64_t k = std::min<int64_t>(l, n);
@@ -268,7 +299,7 @@ int rsvd_device(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda
   double* Bt = c->tmp_ws.ptr;
   double* Q = Bt + (size_t)n * l;
   double* Ut = Q + (size_t)m * l;
-  RSVDB_TRY(range_finder(c, A, m, n, lda, Omega, ldo, l, q, Q, m));                 // Stage A          src/rSVD.cpp:84-85
+  RSVDB_TRY(range_finder(c, A, m, n, lda, Omega, ldo, l, q, Q, m, up));             // Stage A          src/rSVD.cpp:84-85
   RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, m, l, Bt, n, 0, true));               // B^T = A^T Q      :89 (stored transposed)
   if (method == 1) {
     RSVDB_TRY(small_svd_power_t(c, Bt, n, l, n, 0, seed, Ut, l, l, S, V, ldv, nullptr));   // SVD<Power>(B)    :105-112

@@ -10,10 +10,18 @@ namespace rsvdb {
 // (leading dimension l), valid until the next QR on this context.
 int qr_inplace(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bool sharded, const double** R);
 
+// A still lives in host memory when the path starts (the host-pointer entry points): the upload is cut into row blocks
+// on the side stream and the first product Y = A * Omega consumes each block as it lands, so all but the last block's
+// share of that pass hides under the PCIe transfer.
+struct HostUpload {
+  const double* A = nullptr;   // host matrix, column-major
+  int64_t lda = 0;
+};
+
 // intermediate_step (reference src/rSVD.cpp:57-70): Q <- range finder with q power iterations.  A is this rank's row
-// block (m_local x n).  Q is m_local x l.
+// block (m_local x n).  Q is m_local x l.  up != nullptr: the device buffer A is filled from up->A on the way.
 int range_finder(rsvdb_ctx* c, const double* A, int64_t m_local, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
-                 int l, int q, double* Q, int64_t ldq);
+                 int l, int q, double* Q, int64_t ldq, const HostUpload* up = nullptr);
 
 // SVD<Jacobi|ParallelJacobi> (include/SVD_class.hpp:101-180, :224-333) of a device matrix M (r x c, ldm), or of its
 // transpose when Mt != nullptr is given instead (c x r, ldmt).  U r x k, S k, V c x k, k = min(r,c).
@@ -22,7 +30,8 @@ int small_svd_jacobi(rsvdb_ctx* c, const double* M, int64_t ldm, const double* M
 
 // rSVD (src/rSVD.cpp:72-133) on device data; A is this rank's row block.  U m_local x k, S k, V n x k, k = min(l, n).
 int rsvd_device(rsvdb_ctx* c, const double* A, int64_t m_local, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
-                int l, int q, int method, double* U, int64_t ldu, double* S, double* V, int64_t ldv, uint64_t seed);
+                int l, int q, int method, double* U, int64_t ldu, double* S, double* V, int64_t ldv, uint64_t seed,
+                const HostUpload* up = nullptr);
 
 // SVD<Power> (include/SVD_class.hpp:184-219 + src/PM.cpp) -- power.cu.  Mt is the TRANSPOSE (c x r) of the data matrix
 // and is deflated in place.  U r x r (identity-completed), S min(r,c), V c x dim (columns = right singular vectors).

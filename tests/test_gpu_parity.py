@@ -521,3 +521,37 @@ def test_device_entry_points_stay_inside_their_buffers(engine):
         assert intact(bu, m * l) and intact(bv, n * l) and intact(bs, l), (m, n, l)
         assert bool(torch.isfinite(S).all().item()) and bool((S[:-1] >= S[1:]).all().item())
     engine.lib.rsvdb_use_own_stream(engine.h)
+
+
+@pytest.mark.parametrize("m,n,l", [(40001, 520, 24), (70000, 1000, 100)])
+def test_host_entry_point_uploads_in_row_blocks(engine, oracle, m, n, l):
+    """rsvdb_rsvd_host cuts the upload of A into row blocks under the first product (>= 128 MB inputs): same answer as
+    the single-shot device path and as the oracle's sigma, with an odd row count and a padded host leading dimension."""
+    import torch
+    rng = np.random.default_rng(77)
+    lda = m + 3
+    buf = np.zeros((lda, n), order="F")
+    X = rng.standard_normal((m, 40)); Y = rng.standard_normal((n, 40))
+    buf[:m] = (X * (0.7 ** np.arange(40))) @ Y.T + 1e-9 * rng.standard_normal((m, n))
+    A = buf[:m]                                   # a view with ld = lda
+    Om = W.omega(n, l)
+    U = np.zeros((m, l), order="F"); S = np.zeros(l); V = np.zeros((n, l), order="F")
+    engine.rsvd_host_raw(A.ctypes.data, m, n, lda, Om.ctypes.data, n, 0, l, 2, SVDMethod.Jacobi, U.ctypes.data, m, S.ctypes.data,
+                         V.ctypes.data, n)
+    Ad = torch.from_numpy(np.ascontiguousarray(A.T)).cuda(); Od = torch.from_numpy(np.ascontiguousarray(Om.T)).cuda()
+    Ud = torch.empty((l, m), dtype=torch.float64, device="cuda"); Vd = torch.empty((l, n), dtype=torch.float64, device="cuda")
+    Sd = torch.empty(l, dtype=torch.float64, device="cuda")
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    engine.rsvd_dev(Ad.data_ptr(), m, n, m, Od.data_ptr(), n, l, 2, SVDMethod.Jacobi, Ud.data_ptr(), m, Sd.data_ptr(), Vd.data_ptr(), n)
+    torch.cuda.synchronize()
+    engine.lib.rsvdb_use_own_stream(engine.h)
+    assert oracle.sigma_close(S, Sd.cpu().numpy())[0]
+    Qh = engine.intermediate_step(A, Om, l, 2)
+    assert np.linalg.norm(Qh.T @ Qh - np.eye(l)) < 1e-11
+    r = 40 if l >= 40 else l
+    assert oracle.subspace_sin_theta(Qh[:, :r] if l <= 40 else U[:, :r], U[:, :r]) < 1e-6
+    err = np.linalg.norm(A - (U * S) @ V.T); ref = np.linalg.norm(A - (Ud.cpu().numpy().T * Sd.cpu().numpy()) @ Vd.cpu().numpy())
+    assert abs(err - ref) <= 1e-8 * np.linalg.norm(A)
+    if l >= 40:
+        sv = np.linalg.svd(A, compute_uv=False)[:40]
+        assert oracle.sigma_close(S[:40], sv)[0]
