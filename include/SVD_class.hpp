@@ -53,6 +53,8 @@ class SVD {
 
  protected:
   void setData(const Mat_m& data) { data_ = data; }   // :67-70 (used by PCA<method> : SVD<method>)
+  // additive, for PCA<method>: the fused centre + SVD entry point (rsvdb_pca_host) delivers the factors directly
+  void setResults(const Mat_m& U, const Vec_v& S, const Mat_m& V) { U_ = U; S_ = S; V_ = V; }
 };
 
 #endif  // SVD_CLASS_HPP

@@ -144,6 +144,44 @@ RSVDB_API int rsvdb_rsvd_csr_dev(rsvdb_ctx* ctx, int64_t m, int64_t n, int64_t n
 RSVDB_API int rsvdb_csr_spmm_dev(rsvdb_ctx* ctx, int64_t m, const int64_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
                                  const double* dX_rowmajor, int l, double* dY_rowmajor);
 
+/* ---- PCA front / back steps around the path ----------------------------------------------------
+ * Reference: PCA/include/PCA_class.hpp.  data is m x n, rows = observations, columns = variables. */
+
+/* PCA<method>(data, normalize)::initialize() (PCA_class.hpp:24-47): column means (:33), centring (:34), optional division
+ * by the sample standard deviation (:38-41), then SVD<method> of the centred matrix (:45-46) -- one upload, everything
+ * on the device.  Outputs as rsvdb_svd_host (same shapes per method); mean[n]; stddev[n] is written only when
+ * normalize != 0 (may be NULL otherwise).  Fewer than 2 rows or 2 columns: RSVDB_ERR_INVALID_ARGUMENT with the
+ * reference's message (assertDataValid, :50-54). */
+RSVDB_API int rsvdb_pca_host(rsvdb_ctx* ctx, const double* data, int64_t m, int64_t n, int64_t ld, int normalize, int method, int r,
+                             uint64_t seed, double* mean, double* stddev, double* U, int64_t ldu, double* S, double* V,
+                             int64_t ldv, int* found);
+
+/* Column statistics of device data (row shard): mean[j] (PCA_class.hpp:33) and, when d_stddev != NULL, the sample
+ * standard deviation of the centred column (:39).  Sums are all-reduced over the ranks of rsvdb_comm_init. */
+RSVDB_API int rsvdb_column_stats_dev(rsvdb_ctx* ctx, const double* dA, int64_t m, int64_t n, int64_t lda, double* d_mean,
+                                     double* d_stddev);
+/* In place: A(i,j) <- (A(i,j) - mean[j]) / (d_stddev ? d_stddev[j] : 1)   (PCA_class.hpp:34,40). */
+RSVDB_API int rsvdb_center_columns_dev(rsvdb_ctx* ctx, double* dA, int64_t m, int64_t n, int64_t lda, const double* d_mean,
+                                       const double* d_stddev);
+
+/* Randomized PCA: rSVD (src/rSVD.cpp:72-133) of the centred (and scaled) matrix WITHOUT materialising it -- the six
+ * passes stream the original A and the centring enters as rank-1 corrections of the skinny operands
+ * ((A - 1 mu^T) D X = A (D X) - 1 (mu^T D X)).  d_stddev == NULL: centring only.  Same outputs as rsvdb_rsvd_dev. */
+RSVDB_API int rsvdb_rpca_dev(rsvdb_ctx* ctx, const double* dA, int64_t m, int64_t n, int64_t lda, const double* d_mean,
+                             const double* d_stddev, const double* dOmega, int64_t ldo, int l, int q, int method, double* dU,
+                             int64_t ldu, double* dS, double* dV, int64_t ldv);
+/* Host mirror: upload, column statistics, rsvdb_rpca_dev, download.  Omega == NULL: drawn on the device from seed. */
+RSVDB_API int rsvdb_rpca_host(rsvdb_ctx* ctx, const double* A, int64_t m, int64_t n, int64_t lda, int normalize, const double* Omega,
+                              int64_t ldo, uint64_t seed, int l, int q, int method, double* mean, double* stddev, double* U,
+                              int64_t ldu, double* S, double* V, int64_t ldv);
+
+/* projectToPCA (PCA_class.hpp:93-95): out (r x k) = (data - 1 mean^T) * V,  data r x n, V n x k. */
+RSVDB_API int rsvdb_pca_project_host(rsvdb_ctx* ctx, const double* data, int64_t r, int64_t n, int64_t ld, const double* mean,
+                                     const double* V, int64_t ldv, int k, double* out, int64_t ldout);
+/* reconstructFromPCA (PCA_class.hpp:97-99): out (r x n) = pc * V^T + 1 mean^T,  pc r x k, V n x k. */
+RSVDB_API int rsvdb_pca_reconstruct_host(rsvdb_ctx* ctx, const double* pc, int64_t r, int k, int64_t ldp, const double* mean,
+                                         const double* V, int64_t ldv, int64_t n, double* out, int64_t ldout);
+
 /* Number of power iterations PM runs for an n-column matrix (src/PM.cpp:25-28). */
 RSVDB_API int rsvdb_pm_iterations(int64_t ncols);
 

@@ -14,6 +14,7 @@
 #include "QR.hpp"          // /root/reference/include/QR.hpp
 #include "PM.hpp"          // /root/reference/include/PM.hpp
 #include <mpi.h>           // oracle/eigen_shim/mpi.h
+#include "PCA_class.hpp"   // /root/reference/PCA/include/PCA_class.hpp
 
 namespace {
 Mat_m from_buf(const double* p, long r, long c) { Mat_m m(r, c); std::memcpy(m.data(), p, sizeof(double) * r * c); return m; }
@@ -24,6 +25,25 @@ struct Quiet {  // the reference prints from library code (include/SVD_class.hpp
   ~Quiet() { std::cout.rdbuf(old); }
 };
 }  // namespace
+
+// PCA<method>(data, normalize) -- PCA/include/PCA_class.hpp:12-207.  method: 0 Jacobi, 2 ParallelJacobi.  k = min(m, n).
+// Outputs: expl_var[k], ratio[k], scores[m*k], loadings[n*k], mean[n] (= reconstructFromPCA(0), mean_ has no getter),
+// proj[pr*k] = projectToPCA(P), recon[pr*n] = reconstructFromPCA(proj), orth = checkOrthogonality().
+// Returns -1 on the reference's std::invalid_argument (assertDataValid).
+template <SVDMethod M>
+static int ref_pca_t(const Mat_m& d, bool normalize, const Mat_m& P, double* ev, double* ratio, double* scores, double* loadings,
+                     double* mean, double* proj, double* recon, double* orth) {
+  try {
+    PCA<M> pca(d, normalize);
+    to_buf(pca.explainedVariance(), ev); to_buf(pca.explainedVarianceRatio(), ratio);
+    to_buf(pca.scores(), scores); to_buf(pca.loadings(), loadings);
+    const long k = pca.loadings().cols();
+    to_buf(pca.reconstructFromPCA(Mat_m::Zero(1, k)), mean);
+    Mat_m pr = pca.projectToPCA(P); to_buf(pr, proj); to_buf(pca.reconstructFromPCA(pr), recon);
+    *orth = pca.checkOrthogonality();
+  } catch (const std::invalid_argument&) { return -1; }
+  return 0;
+}
 
 extern "C" {
 
@@ -96,6 +116,17 @@ int ref_make_jacobi(double x, double y, double z, double* c, double* s) {
 }
 void ref_real_2x2_jacobi_svd(const double* M4_colmajor, double* cl, double* sl, double* cr, double* sr) {
   Mat_m m = from_buf(M4_colmajor, 2, 2); real_2x2_jacobi_svd(m, *cl, *sl, *cr, *sr, 0, 1);
+}
+
+
+// PCA<method> through the reference's own class (see ref_pca_t above)
+int ref_pca(const double* data, long m, long n, int normalize, int method, const double* P, long pr, double* ev, double* ratio,
+            double* scores, double* loadings, double* mean, double* proj, double* recon, double* orth) {
+  Quiet quiet;
+  Mat_m d = from_buf(data, m, n), p = from_buf(P, pr, n);
+  if (method == 0) return ref_pca_t<SVDMethod::Jacobi>(d, normalize != 0, p, ev, ratio, scores, loadings, mean, proj, recon, orth);
+  if (method == 2) return ref_pca_t<SVDMethod::ParallelJacobi>(d, normalize != 0, p, ev, ratio, scores, loadings, mean, proj, recon, orth);
+  return -2;
 }
 
 }  // extern "C"

@@ -11,6 +11,8 @@ What is restated (reference file:line, relative to /root/reference):
 * small SVD back-ends    include/SVD_class.hpp:101-180 (Jacobi), :224-333 (ParallelJacobi), :184-219 + src/PM.cpp
                          (Power) -- the loops live in oracle/oracle_c.c
 * Givens QR              src/QR.cpp:12-80, manualMatrixMultiply src/matrixOperations.cpp:7-28 -- oracle_c.c
+* ``PCA``                PCA/include/PCA_class.hpp:24-47 (centre, optional stddev scaling, SVD<method>), :76-100
+                         (explained variance / ratio, scores, loadings, projectToPCA, reconstructFromPCA)
 
 Third-party arithmetic: the reference calls Eigen (un-vendored, un-pinned: Makefile:2 ``-I ${mkEigenInc}``) for the dense
 products and ``Eigen::HouseholderQR``.  Eigen is absent from this image.  Its published algorithm (unblocked/blocked
@@ -46,7 +48,8 @@ def build(force: bool = False) -> Path:
     if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
         subprocess.run(["make", "-C", str(_HERE), "oracle_c"], check=True, capture_output=True)
     ref_so = _HERE / "_ref" / "libref_rsvd.so"
-    if Path("/root/reference/src").is_dir() and (force or not ref_so.exists()):
+    drv = _HERE / "ref_driver.cpp"
+    if Path("/root/reference/src").is_dir() and (force or not ref_so.exists() or ref_so.stat().st_mtime < drv.stat().st_mtime):
         subprocess.run(["make", "-C", str(_HERE), "ref"], check=True, capture_output=True)
     return so
 
@@ -161,6 +164,47 @@ def rsvd(A, Omega, l: int, q: int = 2, method: int = JACOBI, seed: int = 0):
 # ---------------------------------------------------------------------------------------------------------------
 # Givens QR / naive GEMM (API-surface helpers)
 # ---------------------------------------------------------------------------------------------------------------
+class PCA:
+    """PCA<method>(data, normalize) -- PCA/include/PCA_class.hpp.  The SVD is the Jacobi / ParallelJacobi restatement
+    above; the front/back steps are the reference's arithmetic written in numpy."""
+
+    def __init__(self, data, normalize: bool = False, method: int = JACOBI):
+        data = np.array(data, dtype=np.float64)
+        if data.shape[0] < 2 or data.shape[1] < 2:                       # assertDataValid, :50-54
+            raise ValueError("PCA requires at least 2 rows and 2 columns.")
+        self.rows = data.shape[0]
+        self.mean = data.sum(axis=0) / data.shape[0]                     # :33  colwise().mean()
+        c = data - self.mean                                             # :34
+        self.stddev = None
+        if normalize:
+            self.stddev = np.sqrt((c * c).sum(axis=0) / (data.shape[0] - 1))   # :39
+            c = c / self.stddev                                          # :40
+        self.centered = c
+        self.U, self.S, self.V, _ = (svd_jacobi if method == JACOBI else svd_parallel_jacobi)(c)   # :45-46
+
+    def explainedVariance(self):                                         # :76-79
+        return self.S / np.sqrt(self.rows - 1)
+
+    def explainedVarianceRatio(self):                                    # :81-84
+        v = self.explainedVariance()
+        return (v * v / (self.rows - 1)) / ((v * v).sum() / (self.rows - 1))
+
+    def scores(self):                                                    # :86-88
+        return self.U * self.S
+
+    def loadings(self):                                                  # :90-92
+        return self.V
+
+    def projectToPCA(self, data):                                        # :93-95
+        return (np.asarray(data, dtype=np.float64) - self.mean) @ self.V
+
+    def reconstructFromPCA(self, pc):                                    # :97-99
+        return np.asarray(pc, dtype=np.float64) @ self.V.T + self.mean
+
+    def checkOrthogonality(self):                                        # :147-151
+        return float(np.linalg.norm(self.V.T @ self.V - np.eye(self.V.shape[1])))
+
+
 def givens_qr(A, reduced: bool = True):
     """src/QR.cpp:22-80."""
     A = _f(A); m, n = A.shape
@@ -284,3 +328,18 @@ class RefLib:
         sigma = ctypes.c_double(); u = np.zeros(m); v = np.zeros(n)
         self.lib.ref_pm(_p(A), ctypes.c_long(m), ctypes.c_long(n), ctypes.byref(sigma), _p(u), _p(v))
         return sigma.value, u, v
+
+    def pca(self, data, normalize=False, method=JACOBI, project=None):
+        """PCA<method> through the reference's own class (oracle/ref_driver.cpp ref_pca).  Returns a dict."""
+        data = _f(data); m, n = data.shape; k = min(m, n)
+        P = _f(data if project is None else project); pr = P.shape[0]
+        ev = np.zeros(k); ratio = np.zeros(k); scores = np.zeros((m, k), order="F"); load = np.zeros((n, k), order="F")
+        mean = np.zeros(n); proj = np.zeros((pr, k), order="F"); recon = np.zeros((pr, n), order="F"); orth = ctypes.c_double(0)
+        rc = self.lib.ref_pca(_p(data), ctypes.c_long(m), ctypes.c_long(n), ctypes.c_int(int(normalize)), ctypes.c_int(method), _p(P),
+                              ctypes.c_long(pr), _p(ev), _p(ratio), _p(scores), _p(load), _p(mean), _p(proj), _p(recon), ctypes.byref(orth))
+        if rc == -1:
+            raise ValueError("PCA requires at least 2 rows and 2 columns.")
+        if rc != 0:
+            raise ValueError("Unsupported SVD method")
+        return dict(explained_variance=ev, ratio=ratio, scores=scores, loadings=load, mean=mean, project=proj, reconstruct=recon,
+                    orthogonality=orth.value)

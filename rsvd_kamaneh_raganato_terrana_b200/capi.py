@@ -73,6 +73,13 @@ def _declare(lib):
         "rsvdb_intermediate_step_host": [vp, vp, i64, i64, i64, vp, i64, c_int, c_int, vp, i64],
         "rsvdb_generate_omega_host": [vp, i64, c_int, u64, vp, i64],
         "rsvdb_svd_host": [vp, vp, i64, i64, i64, c_int, c_int, u64, vp, i64, vp, vp, i64, POINTER(c_int)],
+        "rsvdb_pca_host": [vp, vp, i64, i64, i64, c_int, c_int, c_int, u64, vp, vp, vp, i64, vp, vp, i64, POINTER(c_int)],
+        "rsvdb_column_stats_dev": [vp, vp, i64, i64, i64, vp, vp],
+        "rsvdb_center_columns_dev": [vp, vp, i64, i64, i64, vp, vp],
+        "rsvdb_rpca_dev": [vp, vp, i64, i64, i64, vp, vp, vp, i64, c_int, c_int, c_int, vp, i64, vp, vp, i64],
+        "rsvdb_rpca_host": [vp, vp, i64, i64, i64, c_int, vp, i64, u64, c_int, c_int, c_int, vp, vp, vp, i64, vp, vp, i64],
+        "rsvdb_pca_project_host": [vp, vp, i64, i64, i64, vp, vp, i64, c_int, vp, i64],
+        "rsvdb_pca_reconstruct_host": [vp, vp, i64, c_int, i64, vp, vp, i64, i64, vp, i64],
         "rsvdb_qr_host": [vp, vp, i64, i64, i64, c_int, vp, i64, vp, i64],
         "rsvdb_pm_host": [vp, vp, i64, i64, i64, u64, POINTER(c_double), vp, vp],
         "rsvdb_gemm_host": [vp, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64],

@@ -6,6 +6,7 @@
 
 #include "comm.cuh"
 #include "context.cuh"
+#include "pca.cuh"
 #include "pipeline.cuh"
 #include "spmm.cuh"
 #include "tsqr.cuh"
@@ -38,6 +39,11 @@ __global__ void k_sign_normalise(double* __restrict__ Q, long long ldq, long lon
   if (!(d < 0.0)) return;
   for (int j = threadIdx.x; j < rcols; j += blockDim.x) R[(size_t)j * ldr + i] = -R[(size_t)j * ldr + i];
   for (long long r = threadIdx.x; r < qrows; r += blockDim.x) Q[(size_t)i * ldq + r] = -Q[(size_t)i * ldq + r];
+}
+
+__global__ void k_reciprocal(const double* __restrict__ x, double* __restrict__ y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = 1.0 / x[i];
 }
 
 inline int64_t even_ld(int64_t rows) { return std::max<int64_t>(2, (rows + 1) & ~int64_t(1)); }
@@ -106,7 +112,7 @@ int rsvdb_destroy(rsvdb_ctx* c) {
   for (auto e : c->side_ev) if (e) cudaEventDestroy(e);
   for (auto& s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (auto e : c->event_pool) cudaEventDestroy(e);
-  c->gemm_ws.release(); c->qr_ws.release(); c->qr2_ws.release(); c->tmp_ws.release(); c->svd_ws.release(); c->io_ws.release(); c->wide_ws.release();
+  c->gemm_ws.release(); c->qr_ws.release(); c->qr2_ws.release(); c->tmp_ws.release(); c->svd_ws.release(); c->io_ws.release(); c->wide_ws.release(); c->pca_ws.release();
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return RSVDB_OK;
@@ -284,8 +290,21 @@ int rsvdb_rsvd_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t
   return RSVDB_OK;
 }
 
-int rsvdb_svd_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, int method, int r, uint64_t seed, double* U,
-                   int64_t ldu, double* S, double* V, int64_t ldv, int* found) {
+}  // extern "C"
+
+namespace {
+// PCA<method>::initialize() pre-pass on the freshly uploaded matrix (PCA/include/PCA_class.hpp:30-41)
+struct PcaPre { int normalize; double* mean; double* stddev; };
+int pca_prepass(rsvdb_ctx* c, double* dA, int64_t m, int64_t n, int64_t ldA, double* dMean, double* dSd, const PcaPre& pre) {
+  RSVDB_TRY(column_stats(c, dA, m, n, ldA, dMean, pre.normalize ? dSd : nullptr, nullptr));
+  RSVDB_TRY(center_columns(c, dA, m, n, ldA, dMean, pre.normalize ? dSd : nullptr));
+  RSVDB_TRY(d2h(c, pre.mean, n, dMean, n, n, 1));
+  if (pre.normalize && pre.stddev) RSVDB_TRY(d2h(c, pre.stddev, n, dSd, n, n, 1));
+  return 0;
+}
+
+int svd_host_impl(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, int method, int r, uint64_t seed, double* U,
+                  int64_t ldu, double* S, double* V, int64_t ldv, int* found, const PcaPre* pre) {
   if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
   if (method != 0 && method != 1 && method != 2) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "Unsupported SVD method");
   if (!A || !U || !S || !V || m <= 0 || n <= 0 || lda < m || ldu < m || ldv < n || r < 0)
@@ -297,12 +316,14 @@ int rsvdb_svd_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t 
     const int dim = r ? r : (int)k;
     if (dim > k) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "SVD<Power>: r larger than min(rows, cols)");
     const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)ldN * m) + IoArena::pad((size_t)ldA * m) +
-                         IoArena::pad((size_t)ldN * dim) + IoArena::pad((size_t)k)) * 8 + 256;
+                         IoArena::pad((size_t)ldN * dim) + IoArena::pad((size_t)k) + 2 * IoArena::pad((size_t)n)) * 8 + 256;
     RSVDB_CUDA(c, c->io_ws.reserve(need));
     IoArena ar(c);
     double* dA = ar.take((size_t)ldA * n); double* dAt = ar.take((size_t)ldN * m); double* dU = ar.take((size_t)ldA * m);
     double* dV = ar.take((size_t)ldN * dim); double* dS = ar.take((size_t)k);
+    double* dMean = ar.take((size_t)n); double* dSd = ar.take((size_t)n);
     RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
+    if (pre) RSVDB_TRY(pca_prepass(c, dA, m, n, ldA, dMean, dSd, *pre));
     RSVDB_TRY(transpose2d(c, dA, ldA, dAt, ldN, m, n));
     int f = 0;
     RSVDB_TRY(small_svd_power_t(c, dAt, ldN, m, n, r, seed, dU, ldA, (int)m, dS, dV, ldN, &f));
@@ -314,18 +335,154 @@ int rsvdb_svd_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t 
     return RSVDB_OK;
   }
   const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)ldA * k) + IoArena::pad((size_t)ldN * k) +
-                       IoArena::pad((size_t)k)) * 8 + 256;
+                       IoArena::pad((size_t)k) + 2 * IoArena::pad((size_t)n)) * 8 + 256;
   RSVDB_CUDA(c, c->io_ws.reserve(need));
   IoArena ar(c);
   double* dA = ar.take((size_t)ldA * n); double* dU = ar.take((size_t)ldA * k); double* dV = ar.take((size_t)ldN * k);
   double* dS = ar.take((size_t)k);
+  double* dMean = ar.take((size_t)n); double* dSd = ar.take((size_t)n);
   RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
+  if (pre) RSVDB_TRY(pca_prepass(c, dA, m, n, ldA, dMean, dSd, *pre));
   RSVDB_TRY(small_svd_jacobi(c, dA, ldA, nullptr, 0, m, n, dU, ldA, dS, dV, ldN));
   RSVDB_TRY(d2h(c, U, ldu, dU, ldA, m, k));
   RSVDB_TRY(d2h(c, S, k, dS, k, k, 1));
   RSVDB_TRY(d2h(c, V, ldv, dV, ldN, n, k));
   RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
   if (found) *found = (int)k;
+  return RSVDB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rsvdb_svd_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, int method, int r, uint64_t seed, double* U,
+                   int64_t ldu, double* S, double* V, int64_t ldv, int* found) {
+  return svd_host_impl(c, A, m, n, lda, method, r, seed, U, ldu, S, V, ldv, found, nullptr);
+}
+
+int rsvdb_pca_host(rsvdb_ctx* c, const double* data, int64_t m, int64_t n, int64_t ld, int normalize, int method, int r, uint64_t seed,
+                   double* mean, double* stddev, double* U, int64_t ldu, double* S, double* V, int64_t ldv, int* found) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (m < 2 || n < 2) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "PCA requires at least 2 rows and 2 columns.");   // PCA_class.hpp:50-54
+  if (!mean) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "PCA: mean output is required");
+  const PcaPre pre{normalize, mean, stddev};
+  return svd_host_impl(c, data, m, n, ld, method, r, seed, U, ldu, S, V, ldv, found, &pre);
+}
+
+int rsvdb_column_stats_dev(rsvdb_ctx* c, const double* dA, int64_t m, int64_t n, int64_t lda, double* d_mean, double* d_stddev) {
+  if (!c || !dA || !d_mean || m <= 0 || n <= 0 || lda < m) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "column_stats: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  return column_stats(c, dA, m, n, lda, d_mean, d_stddev, nullptr);
+}
+
+int rsvdb_center_columns_dev(rsvdb_ctx* c, double* dA, int64_t m, int64_t n, int64_t lda, const double* d_mean, const double* d_stddev) {
+  if (!c || !dA || !d_mean || m < 0 || n <= 0 || lda < m) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "center_columns: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  return center_columns(c, dA, m, n, lda, d_mean, d_stddev);
+}
+
+int rsvdb_rpca_dev(rsvdb_ctx* c, const double* dA, int64_t m, int64_t n, int64_t lda, const double* d_mean, const double* d_stddev,
+                   const double* dOmega, int64_t ldo, int l, int q, int method, double* dU, int64_t ldu, double* dS, double* dV,
+                   int64_t ldv) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (method != 0 && method != 1 && method != 2) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "Unsupported SVD method");
+  if (!dA || !d_mean || !dOmega || !dU || !dS || !dV || m < 0 || n <= 0 || l <= 0 || q < 0 || lda < m || ldo < n || ldu < m || ldv < n)
+    return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "rPCA: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  RSVDB_CUDA(c, c->pca_ws.reserve(PcaScratch::total(n, l) * sizeof(double)));
+  Centering cen; cen.mu = d_mean;
+  if (d_stddev) {
+    double* inv = c->pca_ws.ptr + PcaScratch::inv_sd_off(n);
+    k_reciprocal<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_stddev, inv, n);
+    RSVDB_CUDA(c, cudaGetLastError()); ++c->launches;
+    cen.inv_sd = inv;
+  }
+  return rsvd_device(c, dA, m, n, lda, dOmega, ldo, l, q, method, dU, ldu, dS, dV, ldv, 0, nullptr, &cen);
+}
+
+int rsvdb_rpca_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, int normalize, const double* Omega, int64_t ldo,
+                    uint64_t seed, int l, int q, int method, double* mean, double* stddev, double* U, int64_t ldu, double* S, double* V,
+                    int64_t ldv) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (method != 0 && method != 1 && method != 2) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "Unsupported SVD method");
+  if (m < 2 || n < 2) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "PCA requires at least 2 rows and 2 columns.");
+  if (!A || !U || !S || !V || !mean || l <= 0 || q < 0 || lda < m || (Omega && ldo < n) || ldu < m || ldv < n)
+    return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "rPCA: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t k = std::min<int64_t>(l, n);
+  const int64_t ldA = even_ld(m), ldO = even_ld(n);
+  const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)ldO * l) + IoArena::pad((size_t)ldA * l) +
+                       IoArena::pad((size_t)ldO * l) + IoArena::pad((size_t)l) + 2 * IoArena::pad((size_t)n)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  RSVDB_CUDA(c, c->pca_ws.reserve(PcaScratch::total(n, l) * sizeof(double)));
+  IoArena ar(c);
+  double* dA = ar.take((size_t)ldA * n); double* dO = ar.take((size_t)ldO * l); double* dU = ar.take((size_t)ldA * l);
+  double* dV = ar.take((size_t)ldO * l); double* dS = ar.take((size_t)l);
+  double* dMean = ar.take((size_t)n); double* dSd = ar.take((size_t)n);
+  RSVDB_TRY(h2d(c, dA, ldA, A, lda, m, n));
+  if (Omega) { RSVDB_TRY(h2d(c, dO, ldO, Omega, ldo, n, l)); }
+  else { RSVDB_TRY(rsvdb_generate_omega_dev(c, n, l, seed, dO, ldO)); }
+  double* inv = normalize ? c->pca_ws.ptr + PcaScratch::inv_sd_off(n) : nullptr;
+  RSVDB_TRY(column_stats(c, dA, m, n, ldA, dMean, normalize ? dSd : nullptr, inv));
+  Centering cen; cen.mu = dMean; cen.inv_sd = inv;
+  RSVDB_TRY(rsvd_device(c, dA, m, n, ldA, dO, ldO, l, q, method, dU, ldA, dS, dV, ldO, seed, nullptr, &cen));
+  RSVDB_TRY(d2h(c, mean, n, dMean, n, n, 1));
+  if (normalize && stddev) RSVDB_TRY(d2h(c, stddev, n, dSd, n, n, 1));
+  RSVDB_TRY(d2h(c, U, ldu, dU, ldA, m, k));
+  RSVDB_TRY(d2h(c, S, k, dS, k, k, 1));
+  RSVDB_TRY(d2h(c, V, ldv, dV, ldO, n, k));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_pca_project_host(rsvdb_ctx* c, const double* data, int64_t r, int64_t n, int64_t ld, const double* mean, const double* V,
+                           int64_t ldv, int k, double* out, int64_t ldout) {
+  if (!c || !data || !mean || !V || !out || r <= 0 || n <= 0 || k <= 0 || ld < r || ldv < n || ldout < r)
+    return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "projectToPCA: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t ldR = even_ld(r), ldN = even_ld(n);
+  const size_t need = (IoArena::pad((size_t)ldR * n) + IoArena::pad((size_t)ldN * k) + IoArena::pad((size_t)ldR * k) + IoArena::pad((size_t)n) +
+                       IoArena::pad((size_t)k)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  double* dD = ar.take((size_t)ldR * n); double* dV = ar.take((size_t)ldN * k); double* dOut = ar.take((size_t)ldR * k);
+  double* dMean = ar.take((size_t)n); double* dw = ar.take((size_t)k);
+  RSVDB_TRY(h2d(c, dD, ldR, data, ld, r, n));
+  RSVDB_TRY(h2d(c, dV, ldN, V, ldv, n, k));
+  RSVDB_TRY(h2d(c, dMean, n, mean, n, n, 1));
+  int nl = 0;                                                    // (data - 1 mean^T) V = data V - 1 (mean^T V)
+  RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, dD, r, n, ldR, dV, ldN, k, dOut, ldR, &nl));
+  c->launches += nl;
+  RSVDB_TRY(weighted_colsum(c, dV, ldN, n, k, dMean, dw));
+  RSVDB_TRY(sub_col_const(c, dOut, ldR, r, k, dw));
+  RSVDB_TRY(d2h(c, out, ldout, dOut, ldR, r, k));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_pca_reconstruct_host(rsvdb_ctx* c, const double* pc, int64_t r, int k, int64_t ldp, const double* mean, const double* V,
+                               int64_t ldv, int64_t n, double* out, int64_t ldout) {
+  if (!c || !pc || !mean || !V || !out || r <= 0 || n <= 0 || k <= 0 || ldp < r || ldv < n || ldout < r)
+    return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "reconstructFromPCA: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t ldR = even_ld(r), ldN = even_ld(n), ldK = even_ld(k);
+  const size_t need = (IoArena::pad((size_t)ldR * k) + IoArena::pad((size_t)ldN * k) + IoArena::pad((size_t)ldK * n) + IoArena::pad((size_t)ldR * n) +
+                       IoArena::pad((size_t)n)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  double* dP = ar.take((size_t)ldR * k); double* dV = ar.take((size_t)ldN * k); double* dVt = ar.take((size_t)ldK * n);
+  double* dOut = ar.take((size_t)ldR * n); double* dMean = ar.take((size_t)n);
+  RSVDB_TRY(h2d(c, dP, ldR, pc, ldp, r, k));
+  RSVDB_TRY(h2d(c, dV, ldN, V, ldv, n, k));
+  RSVDB_TRY(h2d(c, dMean, n, mean, n, n, 1));
+  RSVDB_TRY(transpose2d(c, dV, ldN, dVt, ldK, n, k));           // V^T (k x n) as the right operand
+  int nl = 0;
+  if (n <= INT32_MAX) RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, dP, r, k, ldR, dVt, ldK, (int)n, dOut, ldR, &nl));
+  c->launches += nl;
+  RSVDB_TRY(add_row_vector(c, dOut, ldR, r, n, dMean, 1.0));
+  RSVDB_TRY(d2h(c, out, ldout, dOut, ldR, r, n));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RSVDB_OK;
 }
 

@@ -176,21 +176,40 @@ int qr_inplace(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bool s
   return 0;
 }
 
+static double* cen_xs(rsvdb_ctx* c, int64_t n) { return c->pca_ws.ptr + PcaScratch::xs_off(n); }   // layout: pca.cuh
+
 static int gemm_an_phase(rsvdb_ctx* c, const double* A, int64_t M, int64_t K, int64_t lda, const double* X, int64_t ldx, int N,
-                         double* Y, int64_t ldy) {
-  PhaseTimer pt(c, PH_GEMM_AN);
-  int k = 0;
-  RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, A, M, K, lda, X, ldx, N, Y, ldy, &k));
-  c->launches += k;
+                         double* Y, int64_t ldy, const Centering* cen = nullptr) {
+  double* w = nullptr;
+  if (cen) {                                                 // Ac X = A (D X) - 1 (mu^T D X)
+    PhaseTimer po(c, PH_OTHER);
+    double* Xs = cen_xs(c, K); w = Xs + PcaScratch::pad((size_t)K * N);
+    if (cen->inv_sd) { RSVDB_TRY(scale_rows_copy(c, X, ldx, Xs, K, K, N, cen->inv_sd)); X = Xs; ldx = K; }
+    RSVDB_TRY(weighted_colsum(c, X, ldx, K, N, cen->mu, w));
+  }
+  {
+    PhaseTimer pt(c, PH_GEMM_AN);
+    int k = 0;
+    RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, A, M, K, lda, X, ldx, N, Y, ldy, &k));
+    c->launches += k;
+  }
+  if (cen) { PhaseTimer po(c, PH_OTHER); RSVDB_TRY(sub_col_const(c, Y, ldy, M, N, w)); }
   return 0;
 }
 static int gemm_at_phase(rsvdb_ctx* c, const double* A, int64_t K, int64_t M, int64_t lda, const double* Q, int64_t ldq, int N,
-                         double* Z, int64_t ldz, int transpose_out, bool reduce) {
+                         double* Z, int64_t ldz, int transpose_out, bool reduce, const Centering* cen = nullptr) {
   {
     PhaseTimer pt(c, PH_GEMM_AT);
     int k = 0;
     RSVDB_CUDA(c, gemm_at(c->gemm_ws, c->stream, c->nsm, A, K, M, lda, Q, ldq, N, Z, ldz, transpose_out, &k));
     c->launches += k;
+  }
+  if (cen) {                                                 // Ac^T Q = D (A^T Q - mu (1^T Q)); linear, so it is applied per shard
+    if (transpose_out) return fail(c, -1, "implicit centring expects the M x N output layout");
+    PhaseTimer po(c, PH_OTHER);
+    double* sv = cen_xs(c, M) + PcaScratch::pad((size_t)M * N) + PcaScratch::pad((size_t)N);
+    RSVDB_TRY(weighted_colsum(c, Q, ldq, K, N, nullptr, sv));
+    RSVDB_TRY(rank1_correct(c, Z, ldz, M, N, cen->mu, sv, cen->inv_sd));
   }
   if (reduce && c->nranks > 1) {
     // A^T Q = sum over row shards of A_p^T Q_p; Z is contiguous (ldz == M or N) by construction in this file
@@ -227,21 +246,24 @@ static int upload_and_first_pass(rsvdb_ctx* c, double* A, int64_t m, int64_t n, 
 }
 
 int range_finder(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
-                 int l, int q, double* Q, int64_t ldq, const HostUpload* up) {
+                 int l, int q, double* Q, int64_t ldq, const HostUpload* up, const Centering* cen) {
   if (l <= 0 || q < 0) return fail(c, -1, "range_finder: l must be positive and q non-negative");
   // Z (n x l) lives in tmp_ws at offset 0
   RSVDB_CUDA(c, c->tmp_ws.reserve(std::max<size_t>(c->tmp_ws.bytes, (size_t)n * l * sizeof(double))));
   double* Z = c->tmp_ws.ptr;
+  if (cen && c->pca_ws.bytes < PcaScratch::total(n, l) * sizeof(double))
+    return fail(c, -1, "range_finder: reserve pca_ws (PcaScratch::total) before building a Centering");
   if (up && up->A && m > 0) {
+    if (cen) return fail(c, -1, "range_finder: the blocked upload and implicit centring are separate entry points");
     RSVDB_TRY(upload_and_first_pass(c, const_cast<double*>(A), m, n, lda, *up, Omega, ldo, l, Q, ldq));
   } else {
-    RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Omega, ldo, l, Q, ldq));          // Y = A * Omega          src/rSVD.cpp:59
+    RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Omega, ldo, l, Q, ldq, cen));     // Y = A * Omega          src/rSVD.cpp:59
   }
   RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));                       // Q = qr(Y).Q            :60-61
   for (int it = 0; it < q; ++it) {                                             // :62
-    RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, ldq, l, Z, n, 0, true));       // Y = A^T * Q            :63
+    RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, ldq, l, Z, n, 0, true, cen));  // Y = A^T * Q            :63
     RSVDB_TRY(qr_inplace(c, Z, n, l, n, false, nullptr));                      // Q = qr(Y).Q  (n x l)   :64-65
-    RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Z, n, l, Q, ldq));                // Y = A * Q              :66
+    RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Z, n, l, Q, ldq, cen));           // Y = A * Q              :66
     RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));                     // Q = qr(Y).Q            :67-68
   }
   return 0;
@@ -289,7 +311,7 @@ int small_svd_jacobi(rsvdb_ctx* c, const double* M, int64_t ldm, const double* M
 
 int rsvd_device(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
                 int l, int q, int method, double* U, int64_t ldu, double* S, double* V, int64_t ldv, uint64_t seed,
-                const HostUpload* up) {
+                const HostUpload* up, const Centering* cen) {
   if (method != 0 && method != 1 && method != 2) return fail(c, -1, "Unsupported SVD method");   // src/rSVD.cpp:122-123
   if (l <= 0 || n <= 0 || m < 0) return fail(c, -1, "rSVD: bad shape");
   const int64_t k = std::min<int64_t>(l, n);
@@ -299,8 +321,8 @@ int rsvd_device(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda
   double* Bt = c->tmp_ws.ptr;
   double* Q = Bt + (size_t)n * l;
   double* Ut = Q + (size_t)m * l;
-  RSVDB_TRY(range_finder(c, A, m, n, lda, Omega, ldo, l, q, Q, m, up));             // Stage A          src/rSVD.cpp:84-85
-  RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, m, l, Bt, n, 0, true));               // B^T = A^T Q      :89 (stored transposed)
+  RSVDB_TRY(range_finder(c, A, m, n, lda, Omega, ldo, l, q, Q, m, up, cen));        // Stage A          src/rSVD.cpp:84-85
+  RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, m, l, Bt, n, 0, true, cen));          // B^T = A^T Q      :89 (stored transposed)
   if (method == 1) {
     RSVDB_TRY(small_svd_power_t(c, Bt, n, l, n, 0, seed, Ut, l, l, S, V, ldv, nullptr));   // SVD<Power>(B)    :105-112
   } else {

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include "context.cuh"
+#include "pca.cuh"
 
 namespace rsvdb {
 
@@ -21,7 +22,7 @@ struct HostUpload {
 // intermediate_step (reference src/rSVD.cpp:57-70): Q <- range finder with q power iterations.  A is this rank's row
 // block (m_local x n).  Q is m_local x l.  up != nullptr: the device buffer A is filled from up->A on the way.
 int range_finder(rsvdb_ctx* c, const double* A, int64_t m_local, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
-                 int l, int q, double* Q, int64_t ldq, const HostUpload* up = nullptr);
+                 int l, int q, double* Q, int64_t ldq, const HostUpload* up = nullptr, const Centering* cen = nullptr);
 
 // SVD<Jacobi|ParallelJacobi> (include/SVD_class.hpp:101-180, :224-333) of a device matrix M (r x c, ldm), or of its
 // transpose when Mt != nullptr is given instead (c x r, ldmt).  U r x k, S k, V c x k, k = min(r,c).
@@ -29,9 +30,11 @@ int small_svd_jacobi(rsvdb_ctx* c, const double* M, int64_t ldm, const double* M
                      double* U, int64_t ldu, double* S, double* V, int64_t ldv);
 
 // rSVD (src/rSVD.cpp:72-133) on device data; A is this rank's row block.  U m_local x k, S k, V n x k, k = min(l, n).
+// cen != nullptr: the factorisation is that of (A - 1 mu^T) diag(inv_sd) -- the matrix PCA_class.hpp:30-41 would
+// materialise -- computed from the uncentred A through rank-1 corrections (pca.cuh).
 int rsvd_device(rsvdb_ctx* c, const double* A, int64_t m_local, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
                 int l, int q, int method, double* U, int64_t ldu, double* S, double* V, int64_t ldv, uint64_t seed,
-                const HostUpload* up = nullptr);
+                const HostUpload* up = nullptr, const Centering* cen = nullptr);
 
 // SVD<Power> (include/SVD_class.hpp:184-219 + src/PM.cpp) -- power.cu.  Mt is the TRANSPOSE (c x r) of the data matrix
 // and is deflated in place.  U r x r (identity-completed), S min(r,c), V c x dim (columns = right singular vectors).

@@ -10,9 +10,11 @@ the same surface for Python callers and for the parity tests, with the reference
     qr_decomposition_reduced / _full   include/QR.hpp:15-16     -> (Q, R)
     PM(A)                              include/PM.hpp:18        -> (sigma, u, v)
     manualMatrixMultiply(A, B)         include/matrixOperations.hpp:14
+    PCA(method)(data, normalize)       PCA/include/PCA_class.hpp:11 -> scores / loadings / explainedVariance / projectToPCA ...
 
-Host arrays are numpy float64 (any layout; they are passed column-major like Eigen::MatrixXd).  All arithmetic runs in
-the CUDA library; nothing here computes on the CPU and there is no fallback.
+Host arrays are numpy float64 (any layout; they are passed column-major like Eigen::MatrixXd).  Every factorisation and
+product runs in the CUDA library and there is no fallback; the only host arithmetic is the O(k) / O(m k) getter epilogues
+of PCA (S / sqrt(m-1), U * diag(S)), which the reference also evaluates lazily on returned factors.
 """
 from __future__ import annotations
 
@@ -237,6 +239,53 @@ class Engine:
         return U, S, V
 
 
+    # -- PCA front / back steps (PCA/include/PCA_class.hpp) ------------------------------------------------------------
+    def pca(self, data, normalize: bool = False, method=SVDMethod.Jacobi, r: int = 0, seed: int = 0):
+        """PCA<method>(data, normalize)::initialize() -- PCA_class.hpp:24-47: centre, optionally scale, SVD<method>; one
+        upload.  Returns (mean, stddev or None, U, S, V)."""
+        A = _f(data); m, n = A.shape; k = min(m, n)
+        method = int(method)
+        if method == SVDMethod.Power:
+            raise ValueError("PCA<Power>: scores() is ill-formed in the reference (U is m x m); use Jacobi / ParallelJacobi")
+        mean = np.zeros(n); sd = np.zeros(n)
+        U = np.zeros((m, max(k, 1)), order="F"); S = np.zeros(max(k, 1)); V = np.zeros((n, max(k, 1)), order="F")
+        found = ctypes.c_int()
+        self._check(self.lib.rsvdb_pca_host(self.h, _ptr(A), m, n, max(m, 1), int(bool(normalize)), method, r, seed, _ptr(mean), _ptr(sd),
+                                            _ptr(U), max(m, 1), _ptr(S), _ptr(V), max(n, 1), ctypes.byref(found)))
+        return mean, (sd if normalize else None), U, S, V
+
+    def rpca(self, data, l: int, normalize: bool = False, method=SVDMethod.Jacobi, Omega=None, q: int = 2, seed: int = 0):
+        """Randomized PCA: rSVD of the centred (scaled) matrix without materialising it.  Returns (mean, stddev, U, S, V)."""
+        A = _f(data); m, n = A.shape; k = min(l, n)
+        mean = np.zeros(n); sd = np.zeros(n)
+        U = np.zeros((m, k), order="F"); S = np.zeros(k); V = np.zeros((n, k), order="F")
+        om_ptr, ldo = None, 0
+        if Omega is not None:
+            Omega = _f(Omega)
+            if Omega.shape != (n, l):
+                raise ValueError("Omega must be n x l")
+            om_ptr, ldo = _ptr(Omega), n
+        self._check(self.lib.rsvdb_rpca_host(self.h, _ptr(A), m, n, max(m, 1), int(bool(normalize)), om_ptr, ldo, seed, l, q, int(method),
+                                             _ptr(mean), _ptr(sd), _ptr(U), max(m, 1), _ptr(S), _ptr(V), n))
+        return mean, (sd if normalize else None), U, S, V
+
+    def pca_project(self, data, mean, V):
+        """projectToPCA -- PCA_class.hpp:93-95."""
+        D = _f(data); V = _f(V); r, n = D.shape; k = V.shape[1]
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        out = np.zeros((r, k), order="F")
+        self._check(self.lib.rsvdb_pca_project_host(self.h, _ptr(D), r, n, r, _ptr(mean), _ptr(V), n, k, _ptr(out), r))
+        return out
+
+    def pca_reconstruct(self, pc, mean, V):
+        """reconstructFromPCA -- PCA_class.hpp:97-99."""
+        P = _f(pc); V = _f(V); r, k = P.shape; n = V.shape[0]
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        out = np.zeros((r, n), order="F")
+        self._check(self.lib.rsvdb_pca_reconstruct_host(self.h, _ptr(P), r, k, r, _ptr(mean), _ptr(V), n, n, _ptr(out), r))
+        return out
+
+
 def _power_v_layout(Vcols: np.ndarray, n: int, dim: int, found: int) -> np.ndarray:
     """The Power back-end stores right singular vectors in the ROWS of an identity-initialised n x n matrix
     (include/SVD_class.hpp:83,214)."""
@@ -263,6 +312,86 @@ class SVD:
     def getU(self): return self._U.copy(order="F")     # getters return by value (:46-48)
     def getS(self): return self._S.copy()
     def getV(self): return self._V.copy(order="F")
+
+
+class PCA(SVD):
+    """template<SVDMethod> class PCA : public SVD<method> -- PCA/include/PCA_class.hpp:11-207 (same member names).
+    ``l`` (additive): when given, the decomposition is the rank-l randomized one of ``Engine.rpca`` instead of the full SVD."""
+
+    def __init__(self, engine: Engine, method, data, normalize: bool = False, l: int = 0, Omega=None, q: int = 2):
+        super().__init__(engine, method, data)
+        self._orig = _f(data).copy(order="F")
+        self._normalize = bool(normalize)
+        self._l, self._Omega, self._q = l, Omega, q
+        self.initialize()
+
+    def initialize(self):                                   # :24-47
+        self.assertDataValid()
+        if self._l:
+            self._mean, self._stddev, self._U, self._S, self._V = self._e.rpca(self._orig, self._l, self._normalize, self._method,
+                                                                                 self._Omega, self._q)
+        else:
+            self._mean, self._stddev, self._U, self._S, self._V = self._e.pca(self._orig, self._normalize, self._method)
+
+    def assertDataValid(self):                              # :50-54
+        if self._orig.shape[0] < 2 or self._orig.shape[1] < 2:
+            raise ValueError("PCA requires at least 2 rows and 2 columns.")
+
+    def addData(self, new_data):                            # :57-61
+        self._orig = np.asfortranarray(np.vstack([self._orig, _f(new_data)]))
+        self.initialize()
+
+    def normalizeData(self):                                # :63-66 (scales the stored data by the UNcentred second moment)
+        sd = np.sqrt((self._orig ** 2).sum(axis=0) / (self._orig.shape[0] - 1))
+        self._stddev = sd
+        self._orig = np.asfortranarray(self._orig / sd)
+
+    def setNormalization(self, normalize: bool):            # :69-72
+        self._normalize = bool(normalize)
+        self.initialize()
+
+    def explainedVariance(self):                            # :75-78
+        return self.getS() / np.sqrt(self._orig.shape[0] - 1)
+
+    def explainedVarianceRatio(self):                       # :80-83
+        v = self.explainedVariance(); d = self._orig.shape[0] - 1
+        return (v * v / d) / ((v * v).sum() / d)
+
+    def scores(self):                                       # :85-87
+        return np.asfortranarray(self.getU() * self.getS())
+
+    def loadings(self):                                     # :89-91
+        return self.getV()
+
+    def projectToPCA(self, data):                           # :93-95
+        return self._e.pca_project(data, self._mean, self._V)
+
+    def reconstructFromPCA(self, pc):                       # :97-99
+        return self._e.pca_reconstruct(pc, self._mean, self._V)
+
+    def checkOrthogonality(self) -> float:                  # :147-151
+        V = self.getV()
+        return float(np.linalg.norm(V.T @ V - np.eye(V.shape[1])))
+
+    def mean(self): return self._mean.copy()                # additive: mean_ / stddev_ are private without getters in the reference
+    def stddev(self): return None if self._stddev is None else self._stddev.copy()
+
+    def summary(self) -> str:                               # :153-196 (returned instead of printed)
+        ev = self.explainedVariance(); pr = self.explainedVarianceRatio(); cum = np.cumsum(pr)
+        head = f"{'Component':<25}" + "".join(f"{'Comp.' + str(i + 1):<15}" for i in range(ev.size))
+        rows = [("Standard deviation", ev), ("Proportion of Variance", pr), ("Cumulative Proportion", cum)]
+        return "\n".join(["Importance of components:", head] + [f"{nm:<25}" + "".join(f"{x:<15.6f}" for x in v) for nm, v in rows])
+
+    def saveResults(self, filename):                        # :101-144 (same file layout)
+        cum = np.cumsum(self.explainedVarianceRatio())
+        with open(filename, "w") as f:
+            f.write("\nCumulative Explained Variance:\n")
+            for x in cum:
+                f.write(f"{x:g}\n")
+            for title, M in (("Scores", self.scores()), ("Loadings", self.loadings())):
+                f.write(f"\n{title}:\n")
+                for row in M:
+                    f.write(", ".join(f"{x:g}" for x in row) + "\n")
 
 
 _default = None

@@ -41,9 +41,52 @@ def rsvd_inputs():
     return d
 
 
+def _parse_table(path, skip_cols):
+    """The loaders of PCA/tests/pca_test.cpp:7-57 (tourists: header + 3 label columns) and athletic_test.cpp (header + 1)."""
+    rows = []
+    with open(path) as f:
+        next(f)
+        for line in f:
+            vals = []
+            for tok in line.split()[skip_cols:]:
+                try:
+                    vals.append(float(tok))
+                except ValueError:
+                    pass
+            if vals:
+                rows.append(vals)
+    w = max(len(r) for r in rows)
+    return np.asfortranarray(np.array([r for r in rows if len(r) == w]))
+
+
+def pca_inputs():
+    """name -> (data, rows to project).  The two reference datasets are stored in the fixture (the GPU box has no
+    /root/reference); the synthetic ones are regenerated from seeds."""
+    rng = np.random.default_rng(20260103)
+    ref_data = Path("/root/reference/PCA/data/input")
+    d = {}
+    if ref_data.is_dir():
+        d["tourists"] = _parse_table(ref_data / "tourists.txt", 3)             # PCA/tests/pca_test.cpp
+        d["athletic"] = _parse_table(ref_data / "dataset_athletic.txt", 1)     # PCA/tests/athletic_test.cpp
+    d["offset_500x60"] = np.asfortranarray(W.c3_pca(500, 60, seed=31) * (1.0 + np.arange(60) % 5) + 3.0 * rng.standard_normal(60))
+    d["wide_30x50"] = np.asfortranarray(rng.standard_normal((30, 50)) + rng.uniform(-2, 2, 50))
+    return d
+
+
 def main():
     ref = O.RefLib()
     out = {}
+    for nm, D in pca_inputs().items():
+        if nm in ("tourists", "athletic"):
+            out[f"pca/{nm}/data"] = D
+        for norm in (0, 1):
+            for meth, tag in ((O.JACOBI, "jacobi"), (O.PARALLEL_JACOBI, "pjacobi")):
+                r = ref.pca(D, bool(norm), meth, project=D[:7])
+                for key in ("explained_variance", "ratio", "mean"):
+                    out[f"pca/{nm}/n{norm}/{tag}/{key}"] = r[key]
+                out[f"pca/{nm}/n{norm}/{tag}/abs_scores"] = np.abs(r["scores"])
+                out[f"pca/{nm}/n{norm}/{tag}/abs_project"] = np.abs(r["project"])
+                out[f"pca/{nm}/n{norm}/{tag}/reconstruct"] = r["reconstruct"]
     for nm, (A, l) in rsvd_inputs().items():
         Om = W.omega(A.shape[1], l)
         Q = ref.intermediate_step(A, Om, l, 2)

@@ -555,3 +555,137 @@ def test_host_entry_point_uploads_in_row_blocks(engine, oracle, m, n, l):
     if l >= 40:
         sv = np.linalg.svd(A, compute_uv=False)[:40]
         assert oracle.sigma_close(S[:40], sv)[0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PCA front / back steps (PCA/include/PCA_class.hpp) on the device
+# ---------------------------------------------------------------------------------------------------------------------
+def _pca_cases():
+    g = np.load(Path(__file__).resolve().parent / "golden" / "ref_outputs.npz")
+    d = G.pca_inputs()
+    for nm in ("tourists", "athletic"):
+        d[nm] = np.asfortranarray(g[f"pca/{nm}/data"])
+    return d, g
+
+
+@pytest.mark.parametrize("name", ["tourists", "athletic", "offset_500x60", "wide_30x50"])
+@pytest.mark.parametrize("normalize", [0, 1])
+def test_pca_class_vs_oracle_and_reference_golden(engine, oracle, name, normalize):
+    from rsvd_kamaneh_raganato_terrana_b200 import PCA
+    d, g = _pca_cases()
+    D = d[name]
+    for meth, tag in ((SVDMethod.Jacobi, "jacobi"), (SVDMethod.ParallelJacobi, "pjacobi")):
+        p = PCA(engine, meth, D, bool(normalize))
+        o = oracle.PCA(D, bool(normalize), oracle.JACOBI)
+        key = f"pca/{name}/n{normalize}/{tag}/"
+        ev = g[key + "explained_variance"]
+        tol = 1e-6 if tag == "pjacobi" else 1e-8                   # the reference's ParallelJacobi stops early; ours does not
+        assert np.max(np.abs(p.explainedVariance() - ev)) <= tol * ev[0]
+        assert oracle.sigma_close(p.getS(), o.S)[0]
+        assert np.max(np.abs(p.explainedVarianceRatio() - g[key + "ratio"])) <= tol
+        np.testing.assert_allclose(p.mean(), g[key + "mean"], rtol=1e-13, atol=1e-13 * np.abs(D).max())
+        if normalize:
+            np.testing.assert_allclose(p.stddev(), o.stddev, rtol=1e-13)
+        assert p.checkOrthogonality() < 1e-10
+        S = p.getS()
+        if S[-1] > 1e-8 * S[0]:
+            pr = p.projectToPCA(D[:7]); rec = p.reconstructFromPCA(pr)
+            np.testing.assert_allclose(rec, g[key + "reconstruct"], rtol=0, atol=(1e-5 if tag == "pjacobi" else 1e-9) * np.abs(D).max())
+            np.testing.assert_allclose(np.abs(pr), np.abs(o.projectToPCA(D[:7])), rtol=0, atol=1e-8 * np.abs(pr).max())
+        sep = np.r_[np.abs(np.diff(ev)) > 1e-6 * ev[0], True] & np.r_[True, np.abs(np.diff(ev)) > 1e-6 * ev[0]] & (ev > 1e-8 * ev[0])
+        assert np.max(np.abs(np.abs(p.scores())[:, sep] - g[key + "abs_scores"][:, sep])) <= 1e-5 * ev[0] * np.sqrt(D.shape[0])
+        # scores = centred data * loadings (PCA_class.hpp:85-95)
+        assert np.linalg.norm(p.scores() - o.centered @ p.loadings()) <= 1e-10 * np.linalg.norm(o.centered)
+    with pytest.raises(ValueError, match="at least 2 rows and 2 columns"):
+        PCA(engine, SVDMethod.Jacobi, np.zeros((1, 4)))
+    assert "Importance of components" in p.summary()
+
+
+@pytest.mark.parametrize("m,n,l,normalize", [(20001, 300, 20, 0), (20001, 300, 20, 1), (5000, 1000, 64, 1), (777, 130, 16, 0)])
+def test_randomized_pca_without_materialising_the_centred_matrix(engine, oracle, m, n, l, normalize):
+    """rsvdb_rpca_host: the six passes stream the ORIGINAL matrix; centring / scaling enter as rank-1 corrections.  The
+    answer must be the rSVD of the explicitly centred matrix with the same Omega (the oracle's)."""
+    rng = np.random.default_rng(5)
+    A = W.c3_pca(m, n, seed=9) * (1.0 + (np.arange(n) % 7)) + 4.0 * rng.standard_normal(n)      # offsets ~ the signal
+    Om = W.omega(n, l)
+    mean, sd, U, S, V = engine.rpca(A, l, bool(normalize), SVDMethod.Jacobi, Om, 2)
+    mu = A.sum(axis=0) / m
+    C = A - mu
+    np.testing.assert_allclose(mean, mu, rtol=1e-12, atol=1e-12)
+    if normalize:
+        s = np.sqrt((C * C).sum(axis=0) / (m - 1)); C = C / s
+        np.testing.assert_allclose(sd, s, rtol=1e-12)
+    Uo, So, Vo = oracle.rsvd(C, Om, l, 2, oracle.JACOBI)[:3]
+    check_rsvd(oracle, np.asfortranarray(C), U, S, V, Uo, So, Vo, l)
+    # and the explicit device pipeline (centre in place, then plain rSVD) agrees too
+    import torch
+    dev = torch.device("cuda:0")
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    Ad = torch.from_numpy(np.ascontiguousarray(A.T)).to(dev); Od = torch.from_numpy(np.ascontiguousarray(Om.T)).to(dev)
+    md = torch.empty(n, dtype=torch.float64, device=dev); sdd = torch.empty(n, dtype=torch.float64, device=dev)
+    engine._check(engine.lib.rsvdb_column_stats_dev(engine.h, Ad.data_ptr(), m, n, m, md.data_ptr(), sdd.data_ptr() if normalize else None))
+    Ud = torch.empty((l, m), dtype=torch.float64, device=dev); Vd = torch.empty((l, n), dtype=torch.float64, device=dev)
+    Sd = torch.empty(l, dtype=torch.float64, device=dev)
+    engine._check(engine.lib.rsvdb_rpca_dev(engine.h, Ad.data_ptr(), m, n, m, md.data_ptr(), sdd.data_ptr() if normalize else None, Od.data_ptr(), n,
+                                            l, 2, 0, Ud.data_ptr(), m, Sd.data_ptr(), Vd.data_ptr(), n))
+    torch.cuda.synchronize()
+    assert oracle.sigma_close(Sd.cpu().numpy(), S, rtol=1e-11)[0]                # host and device entry points run the same kernels
+    engine._check(engine.lib.rsvdb_center_columns_dev(engine.h, Ad.data_ptr(), m, n, m, md.data_ptr(), sdd.data_ptr() if normalize else None))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(Ad.cpu().numpy().T, C, rtol=0, atol=1e-13 * np.abs(C).max())
+    engine.rsvd_dev(Ad.data_ptr(), m, n, m, Od.data_ptr(), n, l, 2, SVDMethod.Jacobi, Ud.data_ptr(), m, Sd.data_ptr(), Vd.data_ptr(), n)
+    torch.cuda.synchronize()
+    engine.lib.rsvdb_use_own_stream(engine.h)
+    assert oracle.sigma_close(Sd.cpu().numpy(), S)[0]
+
+
+def test_column_stats_on_unaligned_views(engine):
+    """odd leading dimension / odd row offsets exercise the peel paths of the 16-byte column loads"""
+    import torch
+    dev = torch.device("cuda:0")
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(3)
+    for (m, n, lda, off) in [(1001, 37, 1003, 1), (1000, 5, 1001, 0), (3, 4, 3, 0), (2, 2, 7, 3), (4097, 150, 4097, 0)]:
+        buf = torch.from_numpy(rng.standard_normal(lda * n + 8) * 3 + 1.5).to(dev)
+        A = buf[off:off + lda * n]
+        ref = A.view(n, lda)[:, :m].clone()
+        md = torch.empty(n, dtype=torch.float64, device=dev); sd = torch.empty(n, dtype=torch.float64, device=dev)
+        engine._check(engine.lib.rsvdb_column_stats_dev(engine.h, A.data_ptr(), m, n, lda, md.data_ptr(), sd.data_ptr()))
+        mu = ref.sum(dim=1) / m; s = (((ref - mu[:, None]) ** 2).sum(dim=1) / (m - 1)).sqrt()
+        torch.testing.assert_close(md, mu, rtol=1e-13, atol=1e-13); torch.testing.assert_close(sd, s, rtol=1e-12, atol=1e-13)
+        engine._check(engine.lib.rsvdb_center_columns_dev(engine.h, A.data_ptr(), m, n, lda, md.data_ptr(), sd.data_ptr()))
+        torch.cuda.synchronize()
+        torch.testing.assert_close(A.view(n, lda)[:, :m], (ref - md[:, None]) / sd[:, None], rtol=1e-14, atol=1e-14)
+        if lda > m:   # padding rows untouched
+            pad_before = buf[off:off + lda * n].view(n, lda)[:, m:]
+            assert torch.isfinite(pad_before).all()
+    engine.lib.rsvdb_use_own_stream(engine.h)
+
+
+def test_cpp_pca_header(oracle, tmp_path):
+    """PCA/tests/pca_test.cpp's flow against include/PCA_class.hpp: PCA<ParallelJacobi>(data, normalize), summary, saveResults."""
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "pca_test"; libdir = root / "rsvd_kamaneh_raganato_terrana_b200"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-I", str(root / "include"), "-o", str(exe), str(root / "tests" / "cpp" / "pca_test.cpp"),
+                    "-L", str(libdir), "-lrsvdb", f"-Wl,-rpath,{libdir}"], check=True)
+    d, g = _pca_cases()
+    D = d["tourists"]; m, n = D.shape
+    D.ravel(order="F").tofile(tmp_path / "D.bin")
+    for flag, norm in (("yes", 1), ("no", 0)):
+        out = subprocess.run([str(exe), str(tmp_path / "D.bin"), str(m), str(n), flag, str(tmp_path / f"o{norm}")], check=True, capture_output=True, text=True).stdout
+        rd = lambda name, shape: np.fromfile(tmp_path / f"o{norm}_{name}.bin").reshape(shape, order="F")
+        key = f"pca/tourists/n{norm}/pjacobi/"
+        ev = g[key + "explained_variance"]
+        assert np.max(np.abs(rd("ev", (n,)) - ev)) <= 1e-6 * ev[0]
+        assert np.max(np.abs(rd("ratio", (n,)) - g[key + "ratio"])) <= 1e-6
+        assert np.max(np.abs(np.abs(rd("scores", (m, n))) - g[key + "abs_scores"])) <= 1e-5 * ev[0] * np.sqrt(m)
+        np.testing.assert_allclose(rd("reconstruct", (m, n))[:7], g[key + "reconstruct"], rtol=0, atol=1e-5 * np.abs(D).max())
+        np.testing.assert_allclose(rd("reconstruct", (m, n)), D, rtol=0, atol=1e-9 * np.abs(D).max())   # k = n: lossless
+        evf = g[f"pca/tourists/n{1 - norm}/pjacobi/explained_variance"]
+        assert np.max(np.abs(rd("ev_flipped", (n,)) - evf)) <= 1e-6 * evf[0]
+        assert "Importance of components:" in out and "Cumulative Proportion" in out
+        assert f"after addData: scores {2 * m} x {n}" in out
+        assert "invalid_argument: PCA requires at least 2 rows and 2 columns." in out
+        txt = (tmp_path / f"o{norm}_results.txt").read_text()
+        assert "Cumulative Explained Variance:" in txt and "Scores:" in txt and "Loadings:" in txt

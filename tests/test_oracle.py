@@ -121,3 +121,44 @@ def test_oracle_vs_reference_sources_live(oracle):
         ref.manual_matmul(A, A)
     with pytest.raises(ValueError):
         ref.rsvd(A, Om, 8, 5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PCA front / back steps: the numpy restatement vs the reference's own PCA class (golden)
+# ---------------------------------------------------------------------------------------------------------------------
+def pca_cases():
+    g = GOLD
+    d = G.pca_inputs()
+    for nm in ("tourists", "athletic"):          # reference datasets travel inside the fixture
+        d[nm] = np.asfortranarray(g[f"pca/{nm}/data"])
+    return d, g
+
+
+@pytest.mark.parametrize("name", ["tourists", "athletic", "offset_500x60", "wide_30x50"])
+@pytest.mark.parametrize("normalize", [0, 1])
+def test_pca_restatement_matches_reference_class(oracle, name, normalize):
+    d, g = pca_cases()
+    D = d[name]
+    for meth, tag in ((oracle.JACOBI, "jacobi"), (oracle.PARALLEL_JACOBI, "pjacobi")):
+        p = oracle.PCA(D, bool(normalize), meth)
+        key = f"pca/{name}/n{normalize}/{tag}/"
+        ev = g[key + "explained_variance"]
+        tol = 1e-6 if tag == "pjacobi" else 1e-10                      # ParallelJacobi stops early
+        assert np.max(np.abs(p.explainedVariance() - ev)) <= tol * ev[0]
+        assert np.max(np.abs(p.explainedVarianceRatio() - g[key + "ratio"])) <= tol
+        np.testing.assert_allclose(p.mean, g[key + "mean"], rtol=1e-13, atol=1e-13 * np.abs(D).max())
+        if ev[-1] > 1e-8 * ev[0]:     # a numerically zero component has an arbitrary direction (centred 30 x 50 data has rank 29)
+            rec = p.reconstructFromPCA(p.projectToPCA(D[:7]))
+            np.testing.assert_allclose(rec, g[key + "reconstruct"], rtol=0, atol=(1e-5 if tag == "pjacobi" else 1e-9) * np.abs(D).max())
+        # scores / projections agree up to the sign of each well-separated component
+        sep = np.r_[np.abs(np.diff(ev)) > 1e-6 * ev[0], True] & np.r_[True, np.abs(np.diff(ev)) > 1e-6 * ev[0]] & (ev > 1e-8 * ev[0])
+        sc = np.abs(p.scores())[:, sep]; ref_sc = g[key + "abs_scores"][:, sep]
+        assert np.max(np.abs(sc - ref_sc)) <= 1e-5 * ev[0] * np.sqrt(D.shape[0])
+
+
+def test_pca_rejects_degenerate_input(oracle):
+    with pytest.raises(ValueError, match="at least 2 rows and 2 columns"):
+        oracle.PCA(np.zeros((1, 5)))
+    if oracle.RefLib.available():
+        with pytest.raises(ValueError, match="at least 2 rows and 2 columns"):
+            oracle.RefLib().pca(np.zeros((5, 1)))
