@@ -182,6 +182,26 @@ RSVDB_API int rsvdb_pca_project_host(rsvdb_ctx* ctx, const double* data, int64_t
 RSVDB_API int rsvdb_pca_reconstruct_host(rsvdb_ctx* ctx, const double* pc, int64_t r, int k, int64_t ldp, const double* mean,
                                          const double* V, int64_t ldv, int64_t n, double* out, int64_t ldout);
 
+/* ---- POD wrappers --------------------------------------------------------------------------------
+ * Reference: POD/ParametricDiffusion1D/src/POD.cpp.  S is the Nh x ns snapshot matrix.
+ * variant: 0 naive_POD (:116-134), 1 standard_POD (:136-224), 2 energy_POD (:226-336, needs Xh Nh x Nh),
+ *          3 weight_POD (:338-461, needs Xh and D ns x ns).
+ * svd_type (perform_SVD, :42-114): 0 SVD<Power>(A, r), 1 SVD<Jacobi>, 2 SVD<ParallelJacobi>, 3/4/5 rSVD(A, ..., r, Power /
+ *          Jacobi / ParallelJacobi); anything else: RSVDB_ERR_INVALID_ARGUMENT with the reference's message (it exits).
+ * Omega (optional): the sketch for svd_type 3-5, (columns of the matrix handed to rSVD: ns for the naive variant, else
+ *          min(ns, Nh)) x r; NULL: drawn on the device from seed.
+ * Outputs: W (Nh x *N, the first *N of w_cols_full columns are written), sigma (sigma_len values: the singular values of
+ * the CORRELATION matrix for variants 1-3, exactly what the reference stores), *N = modes kept by the energy criterion
+ * (:203-219).  rsvdb_pod_shape gives w_cols_full / sigma_len for sizing the buffers. */
+RSVDB_API int rsvdb_pod_shape(int variant, int64_t Nh, int64_t ns, int r, int svd_type, int64_t* w_cols_full, int64_t* sigma_len);
+RSVDB_API int rsvdb_pod_host(rsvdb_ctx* ctx, int variant, const double* S, int64_t Nh, int64_t ns, int64_t lds, const double* Xh,
+                             int64_t ldx, const double* D, int64_t ldd, int r, double tol, int svd_type, uint64_t seed,
+                             const double* Omega, int64_t ldo, double* W, int64_t ldw, double* sigma, int* N);
+/* Device-pointer twin: W must hold Nh x w_cols_full, all of which are written; synchronises the stream once. */
+RSVDB_API int rsvdb_pod_dev(rsvdb_ctx* ctx, int variant, const double* dS, int64_t Nh, int64_t ns, int64_t lds, const double* dXh,
+                            int64_t ldx, const double* dD, int64_t ldd, int r, double tol, int svd_type, uint64_t seed,
+                            const double* dOmega, int64_t ldo, double* dW, int64_t ldw, double* d_sigma, int* N);
+
 /* Number of power iterations PM runs for an n-column matrix (src/PM.cpp:25-28). */
 RSVDB_API int rsvdb_pm_iterations(int64_t ncols);
 

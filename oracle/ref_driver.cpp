@@ -15,6 +15,7 @@
 #include "PM.hpp"          // /root/reference/include/PM.hpp
 #include <mpi.h>           // oracle/eigen_shim/mpi.h
 #include "PCA_class.hpp"   // /root/reference/PCA/include/PCA_class.hpp
+#include "POD.hpp"         // /root/reference/POD/ParametricDiffusion1D/src/POD.hpp
 
 namespace {
 Mat_m from_buf(const double* p, long r, long c) { Mat_m m(r, c); std::memcpy(m.data(), p, sizeof(double) * r * c); return m; }
@@ -127,6 +128,32 @@ int ref_pca(const double* data, long m, long n, int normalize, int method, const
   if (method == 0) return ref_pca_t<SVDMethod::Jacobi>(d, normalize != 0, p, ev, ratio, scores, loadings, mean, proj, recon, orth);
   if (method == 2) return ref_pca_t<SVDMethod::ParallelJacobi>(d, normalize != 0, p, ev, ratio, scores, loadings, mean, proj, recon, orth);
   return -2;
+}
+
+
+// POD(S, r, svd_type) / POD(S, r, tol, svd_type) / POD(S, Xh, r, tol, svd_type) / POD(S, Xh, D, r, tol, svd_type)
+// -- POD/ParametricDiffusion1D/src/POD.hpp:26-38, POD.cpp:11-40.  variant 0..3 picks the constructor.  Omega (optional):
+// delivered to rSVD's generateOmega through the MPI stub's one-shot Bcast override (svd_type 3-5).
+// W / sigma capacities are the caller's; dims = {W rows, W cols, sigma size}.
+int ref_pod(int variant, const double* S, long Nh, long ns, const double* Xh, const double* D, int r, double tol, int svd_type,
+            const double* Omega, long om_rows, double* W, double* sigma, long* dims) {
+  Quiet quiet;
+  Mat_m s = from_buf(S, Nh, ns), xh, d, om;
+  if (variant >= 2) xh = from_buf(Xh, Nh, Nh);
+  if (variant == 3) d = from_buf(D, ns, ns);
+  if (Omega) { om = from_buf(Omega, om_rows, r); oracle_mpi_set_bcast_override(om.data(), static_cast<std::size_t>(om_rows) * r); }
+  POD* p = nullptr;
+  switch (variant) {
+    case 0: p = new POD(s, r, svd_type); break;
+    case 1: p = new POD(s, r, tol, svd_type); break;
+    case 2: p = new POD(s, xh, r, tol, svd_type); break;
+    case 3: p = new POD(s, xh, d, r, tol, svd_type); break;
+    default: return -1;
+  }
+  to_buf(p->W, W); to_buf(p->sigma, sigma);
+  dims[0] = p->W.rows(); dims[1] = p->W.cols(); dims[2] = p->sigma.size();
+  delete p;
+  return 0;
 }
 
 }  // extern "C"

@@ -11,6 +11,9 @@ What is restated (reference file:line, relative to /root/reference):
 * small SVD back-ends    include/SVD_class.hpp:101-180 (Jacobi), :224-333 (ParallelJacobi), :184-219 + src/PM.cpp
                          (Power) -- the loops live in oracle/oracle_c.c
 * Givens QR              src/QR.cpp:12-80, manualMatrixMultiply src/matrixOperations.cpp:7-28 -- oracle_c.c
+* ``pod``                POD/ParametricDiffusion1D/src/POD.cpp:42-114 (perform_SVD), :116-134 (naive), :136-224
+                         (standard), :226-336 (energy), :338-461 (weight); Eigen's SelfAdjointEigenSolver::operatorSqrt
+                         and ConjugateGradient are restated through numpy eigh / solve
 * ``PCA``                PCA/include/PCA_class.hpp:24-47 (centre, optional stddev scaling, SVD<method>), :76-100
                          (explained variance / ratio, scores, loadings, projectToPCA, reconstructFromPCA)
 
@@ -159,6 +162,66 @@ def rsvd(A, Omega, l: int, q: int = 2, method: int = JACOBI, seed: int = 0):
     else:
         raise ValueError("Unsupported SVD method")   # std::invalid_argument, :122-123
     return Q @ Ut, S, V                          # :128
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# POD wrappers (POD/ParametricDiffusion1D/src/POD.cpp)
+# ---------------------------------------------------------------------------------------------------------------
+def pod_perform_svd(A, r: int, svd_type: int, Omega=None, seed: int = 0):
+    """perform_SVD, POD.cpp:42-114.  Returns (U, sigma, V) in the layouts the selected back-end produces."""
+    if svd_type == 0:
+        return svd_power(A, r, seed)[:3]
+    if svd_type == 1:
+        return svd_jacobi(A)[:3]
+    if svd_type == 2:
+        return svd_parallel_jacobi(A)[:3]
+    if svd_type in (3, 4, 5):
+        if Omega is None:
+            Omega = np.random.default_rng(seed).standard_normal((A.shape[1], r))
+        return rsvd(A, Omega, r, 2, {3: POWER, 4: JACOBI, 5: PARALLEL_JACOBI}[svd_type], seed)
+    raise ValueError("The svd_type should be in [0,5]. Check 'svd_type' in the parameter file.")     # :87-91 (std::exit there)
+
+
+def _spd_sqrt(X):
+    w, v = np.linalg.eigh(X)
+    return (v * np.sqrt(w)) @ v.T
+
+
+def pod(variant: int, S, r: int, tol: float = 0.0, svd_type: int = 1, Xh=None, D=None, Omega=None, seed: int = 0):
+    """variant 0 naive_POD (:116-134), 1 standard_POD (:136-224), 2 energy_POD (:226-336), 3 weight_POD (:338-461).
+    Returns (W, sigma) as the reference's public members: sigma are the singular values of the CORRELATION matrix for
+    variants 1-3 and the modes are divided by them (:164-166)."""
+    S = np.asarray(S, dtype=np.float64); Nh, ns = S.shape
+    if variant == 0:
+        U, sigma, _ = pod_perform_svd(S, r, svd_type, Omega, seed)
+        return U, sigma
+    Sm = S
+    if ns <= Nh:
+        if variant == 1:
+            C = S.T @ S                                                   # :152
+        else:
+            if variant == 3:
+                Sm = S @ _spd_sqrt(D)                                     # :363-370
+            C = (Sm.T @ Xh) @ Sm                                          # :250, :373
+        U, sigma, V = pod_perform_svd(C, r, svd_type, Omega, seed)
+        W = np.zeros((Nh, r))
+        for i in range(r):
+            W[:, i] = Sm @ V[:, i] / sigma[i]                             # :164-166
+    else:
+        if variant == 1:
+            K = S @ S.T                                                   # :171
+            U, sigma, V = pod_perform_svd(K, r, svd_type, Omega, seed)
+            W = U                                                         # :190
+        else:
+            Xs = _spd_sqrt(Xh)                                            # :272-273
+            K = (((Xs @ S) @ S.T) @ Xs) if variant == 2 else ((((Xs @ S) @ D) @ S.T) @ Xs)   # :279, :408
+            U, sigma, V = pod_perform_svd(K, r, svd_type, Omega, seed)
+            W = np.linalg.solve(Xs, U[:, :r])                             # CG to 1e-12, :296-304
+    s2 = sigma[:r] ** 2                                                   # :203-219
+    den = s2.sum(); N = 0; I = 0.0; num = 0.0
+    while I < (1 - tol ** 2) and N < r:
+        num += s2[N]; I = num / den; N += 1
+    return np.asfortranarray(W[:, :N]), sigma
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -343,3 +406,16 @@ class RefLib:
             raise ValueError("Unsupported SVD method")
         return dict(explained_variance=ev, ratio=ratio, scores=scores, loadings=load, mean=mean, project=proj, reconstruct=recon,
                     orthogonality=orth.value)
+
+    def pod(self, variant, S, r, tol=0.0, svd_type=1, Xh=None, D=None, Omega=None):
+        """The reference's POD class (oracle/ref_driver.cpp ref_pod).  Returns (W, sigma)."""
+        S = _f(S); Nh, ns = S.shape; cap = max(Nh, ns)
+        W = np.zeros(Nh * cap); sigma = np.zeros(cap); dims = (ctypes.c_long * 3)()
+        Xh = _f(Xh) if Xh is not None else None; D = _f(D) if D is not None else None
+        Om = _f(Omega) if Omega is not None else None
+        rc = self.lib.ref_pod(ctypes.c_int(variant), _p(S), ctypes.c_long(Nh), ctypes.c_long(ns), _p(Xh) if Xh is not None else None,
+                              _p(D) if D is not None else None, ctypes.c_int(r), ctypes.c_double(tol), ctypes.c_int(svd_type),
+                              _p(Om) if Om is not None else None, ctypes.c_long(Om.shape[0] if Om is not None else 0), _p(W), _p(sigma), dims)
+        if rc != 0:
+            raise ValueError("bad POD variant")
+        return np.array(W[: dims[0] * dims[1]]).reshape((dims[0], dims[1]), order="F"), sigma[: dims[2]].copy()

@@ -8,6 +8,7 @@
 #include "context.cuh"
 #include "pca.cuh"
 #include "pipeline.cuh"
+#include "pod.cuh"
 #include "spmm.cuh"
 #include "tsqr.cuh"
 
@@ -112,7 +113,7 @@ int rsvdb_destroy(rsvdb_ctx* c) {
   for (auto e : c->side_ev) if (e) cudaEventDestroy(e);
   for (auto& s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (auto e : c->event_pool) cudaEventDestroy(e);
-  c->gemm_ws.release(); c->qr_ws.release(); c->qr2_ws.release(); c->tmp_ws.release(); c->svd_ws.release(); c->io_ws.release(); c->wide_ws.release(); c->pca_ws.release();
+  c->gemm_ws.release(); c->qr_ws.release(); c->qr2_ws.release(); c->tmp_ws.release(); c->svd_ws.release(); c->io_ws.release(); c->wide_ws.release(); c->pca_ws.release(); c->pod_ws.release();
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return RSVDB_OK;
@@ -482,6 +483,56 @@ int rsvdb_pca_reconstruct_host(rsvdb_ctx* c, const double* pc, int64_t r, int k,
   c->launches += nl;
   RSVDB_TRY(add_row_vector(c, dOut, ldR, r, n, dMean, 1.0));
   RSVDB_TRY(d2h(c, out, ldout, dOut, ldR, r, n));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_pod_shape(int variant, int64_t Nh, int64_t ns, int r, int svd_type, int64_t* w_cols_full, int64_t* sigma_len) {
+  PodShape sh;
+  if (variant < 0 || variant > 3 || Nh <= 0 || ns <= 0 || r <= 0 || !pod_shape(variant, Nh, ns, r, svd_type, &sh)) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (w_cols_full) *w_cols_full = sh.w_cols_full;
+  if (sigma_len) *sigma_len = sh.sigma_len;
+  return RSVDB_OK;
+}
+
+int rsvdb_pod_dev(rsvdb_ctx* c, int variant, const double* dS, int64_t Nh, int64_t ns, int64_t lds, const double* dXh, int64_t ldx,
+                  const double* dD, int64_t ldd, int r, double tol, int svd_type, uint64_t seed, const double* dOmega, int64_t ldo,
+                  double* dW, int64_t ldw, double* d_sigma, int* N) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (!dS || !dW || !d_sigma || !N || lds < Nh || ldw < Nh) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "POD: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  return pod_device(c, variant, dS, Nh, ns, lds, dXh, ldx, dD, ldd, r, tol, svd_type, seed, dOmega, ldo, dW, ldw, d_sigma, N);
+}
+
+int rsvdb_pod_host(rsvdb_ctx* c, int variant, const double* S, int64_t Nh, int64_t ns, int64_t lds, const double* Xh, int64_t ldx,
+                   const double* D, int64_t ldd, int r, double tol, int svd_type, uint64_t seed, const double* Omega, int64_t ldo,
+                   double* W, int64_t ldw, double* sigma, int* N) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  PodShape sh;
+  if (variant < 0 || variant > 3 || Nh <= 0 || ns <= 0 || r <= 0) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "POD: bad argument");
+  if (!pod_shape(variant, Nh, ns, r, svd_type, &sh))
+    return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "The svd_type should be in [0,5]. Check 'svd_type' in the parameter file.");
+  if (!S || !W || !sigma || !N || lds < Nh || ldw < Nh || (variant >= 2 && (!Xh || ldx < Nh)) || (variant == 3 && (!D || ldd < ns)))
+    return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "POD: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t ldS = even_ld(Nh), ldD = even_ld(ns);
+  const int64_t ob = variant == 0 ? ns : std::min(ns, Nh), ldOm = even_ld(ob);       // rows of Omega
+  if (Omega && ldo < ob) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "POD: Omega leading dimension too small");
+  const size_t need = (IoArena::pad((size_t)ldS * ns) + IoArena::pad((size_t)ldS * sh.w_cols_full) + IoArena::pad((size_t)sh.sigma_len) +
+                       (variant >= 2 ? IoArena::pad((size_t)ldS * Nh) : 0) + (variant == 3 ? IoArena::pad((size_t)ldD * ns) : 0) +
+                       (Omega ? IoArena::pad((size_t)ldOm * r) : 0)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  double* dS = ar.take((size_t)ldS * ns); double* dW = ar.take((size_t)ldS * sh.w_cols_full); double* dSig = ar.take((size_t)sh.sigma_len);
+  double* dX = variant >= 2 ? ar.take((size_t)ldS * Nh) : nullptr; double* dD = variant == 3 ? ar.take((size_t)ldD * ns) : nullptr;
+  double* dOm = Omega ? ar.take((size_t)ldOm * r) : nullptr;
+  RSVDB_TRY(h2d(c, dS, ldS, S, lds, Nh, ns));
+  if (dX) RSVDB_TRY(h2d(c, dX, ldS, Xh, ldx, Nh, Nh));
+  if (dD) RSVDB_TRY(h2d(c, dD, ldD, D, ldd, ns, ns));
+  if (dOm) RSVDB_TRY(h2d(c, dOm, ldOm, Omega, ldo, ob, r));
+  RSVDB_TRY(pod_device(c, variant, dS, Nh, ns, ldS, dX, ldS, dD, ldD, r, tol, svd_type, seed, dOm, ldOm, dW, ldS, dSig, N));
+  RSVDB_TRY(d2h(c, W, ldw, dW, ldS, Nh, *N));             // the basis after conservativeResize(NoChange, N), POD.cpp:221
+  RSVDB_TRY(d2h(c, sigma, sh.sigma_len, dSig, sh.sigma_len, sh.sigma_len, 1));
   RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RSVDB_OK;
 }

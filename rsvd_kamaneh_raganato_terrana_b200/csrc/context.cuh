@@ -23,6 +23,7 @@ struct rsvdb_ctx {
   rsvdb::GemmWorkspace io_ws;       // device copies for the *_host entry points
   rsvdb::GemmWorkspace wide_ws;     // wide-panel QR (l > 100): R, projection coefficients, product buffer
   rsvdb::GemmWorkspace pca_ws;      // column statistics, implicit-centring operands
+  rsvdb::GemmWorkspace pod_ws;      // POD: correlation matrix, SVD factors of it
   int64_t launches = 0;
   std::string err;
   // multi-GPU (row-sharded A); comm is an ncclComm_t resolved at run time (comm.cu)

@@ -11,6 +11,7 @@ the same surface for Python callers and for the parity tests, with the reference
     PM(A)                              include/PM.hpp:18        -> (sigma, u, v)
     manualMatrixMultiply(A, B)         include/matrixOperations.hpp:14
     PCA(method)(data, normalize)       PCA/include/PCA_class.hpp:11 -> scores / loadings / explainedVariance / projectToPCA ...
+    POD(S, [Xh, [D,]] r, [tol,] svd_type)   POD/ParametricDiffusion1D/src/POD.hpp:24 -> .W, .sigma
 
 Host arrays are numpy float64 (any layout; they are passed column-major like Eigen::MatrixXd).  Every factorisation and
 product runs in the CUDA library and there is no fallback; the only host arithmetic is the O(k) / O(m k) getter epilogues
@@ -286,6 +287,27 @@ class Engine:
         return out
 
 
+    # -- POD wrappers (POD/ParametricDiffusion1D/src/POD.cpp) -----------------------------------------------------------
+    def pod(self, variant: int, S, r: int, tol: float = 0.0, svd_type: int = 1, Xh=None, D=None, Omega=None, seed: int = 0):
+        """naive (0) / standard (1) / energy (2) / weight (3) POD -- POD.cpp:116-461; svd_type as perform_SVD (:42-114).
+        Returns (W, sigma): the truncated basis and the singular values exactly as the reference stores them."""
+        S = _f(S); Nh, ns = S.shape
+        wc = ctypes.c_int64(); sl = ctypes.c_int64()
+        if self.lib.rsvdb_pod_shape(int(variant), Nh, ns, int(r), int(svd_type), ctypes.byref(wc), ctypes.byref(sl)) != 0:
+            if not 0 <= int(svd_type) <= 5:
+                raise ValueError("The svd_type should be in [0,5]. Check 'svd_type' in the parameter file.")
+            raise ValueError("POD: bad argument")
+        W = np.zeros((Nh, wc.value), order="F"); sigma = np.zeros(sl.value); N = ctypes.c_int()
+        Xh = _f(Xh) if Xh is not None else None; D = _f(D) if D is not None else None
+        om_ptr, ldo = None, 0
+        if Omega is not None:
+            Omega = _f(Omega); om_ptr, ldo = _ptr(Omega), Omega.shape[0]
+        self._check(self.lib.rsvdb_pod_host(self.h, int(variant), _ptr(S), Nh, ns, Nh, _ptr(Xh) if Xh is not None else None, Nh,
+                                            _ptr(D) if D is not None else None, ns, int(r), float(tol), int(svd_type), seed, om_ptr, ldo,
+                                            _ptr(W), Nh, _ptr(sigma), ctypes.byref(N)))
+        return np.asfortranarray(W[:, :N.value]), sigma
+
+
 def _power_v_layout(Vcols: np.ndarray, n: int, dim: int, found: int) -> np.ndarray:
     """The Power back-end stores right singular vectors in the ROWS of an identity-initialised n x n matrix
     (include/SVD_class.hpp:83,214)."""
@@ -392,6 +414,25 @@ class PCA(SVD):
                 f.write(f"\n{title}:\n")
                 for row in M:
                     f.write(", ".join(f"{x:g}" for x in row) + "\n")
+
+
+class POD:
+    """class POD -- POD/ParametricDiffusion1D/src/POD.hpp:24-70.  The four constructors are told apart by their argument
+    lists like the C++ overloads: (S, r, svd_type) naive; (S, r, tol, svd_type) standard; (S, Xh, r, tol, svd_type) energy;
+    (S, Xh, D, r, tol, svd_type) weight.  Public members W (POD modes) and sigma, as in the reference."""
+
+    def __init__(self, engine: Engine, S, *args, Omega=None, seed: int = 0):
+        if len(args) == 2:
+            variant, Xh, D, (r, svd_type), tol = 0, None, None, args, 0.0
+        elif len(args) == 3:
+            variant, Xh, D, (r, tol, svd_type) = 1, None, None, args
+        elif len(args) == 4:
+            variant, D, (Xh, r, tol, svd_type) = 2, None, args
+        elif len(args) == 5:
+            variant, (Xh, D, r, tol, svd_type) = 3, args
+        else:
+            raise TypeError("POD(S, r, svd_type) | POD(S, r, tol, svd_type) | POD(S, Xh, r, tol, svd_type) | POD(S, Xh, D, r, tol, svd_type)")
+        self.W, self.sigma = engine.pod(variant, S, r, tol, svd_type, Xh, D, Omega, seed)
 
 
 _default = None

@@ -73,9 +73,41 @@ def pca_inputs():
     return d
 
 
+def pod_inputs():
+    """name -> (S, Xh, D, r, tol).  Xh: SPD tridiagonal 'stiffness + mass'-like operator, D: positive quadrature weights."""
+    rng = np.random.default_rng(20260104)
+    def spd(n):
+        return np.asfortranarray(2.0 * np.eye(n) - 0.5 * np.eye(n, k=1) - 0.5 * np.eye(n, k=-1))
+    def weights(n):
+        return np.asfortranarray(np.diag(1.0 + 0.5 * (np.arange(n) % 3)))
+    tall = np.asfortranarray(rng.standard_normal((300, 30)) @ np.diag(0.6 ** np.arange(30)) @ rng.standard_normal((30, 40)))
+    d = {
+        "heat_400x60": (W.c4_pod(400, 60), spd(400), weights(60), 12, 1e-6),
+        "decay_300x40": (tall, spd(300), weights(40), 10, 1e-2),
+        "wide_40x300": (np.asfortranarray(tall.T), spd(40), weights(300), 10, 1e-2),       # ns > Nh branches
+    }
+    return d
+
+
+POD_CASES = [(v, t) for v in (0, 1, 2, 3) for t in (1, 2, 4, 5)]
+
+
+def pod_omega(S, variant, r):
+    Nh, ns = S.shape
+    return W.omega(ns if variant == 0 else min(Nh, ns), r)
+
+
 def main():
     ref = O.RefLib()
     out = {}
+    for nm, (S, Xh, D, r, tol) in pod_inputs().items():
+        for variant, st in POD_CASES:
+            if S.shape[1] > S.shape[0] and variant >= 2 and st <= 2:
+                continue      # the reference writes past U there (POD.cpp:300-302 loops over Utilde.cols() = Nh > r)
+            Wm, sg = ref.pod(variant, S, r, tol, st, Xh if variant >= 2 else None, D if variant == 3 else None,
+                             pod_omega(S, variant, r) if st >= 3 else None)
+            out[f"pod/{nm}/v{variant}/t{st}/sigma"] = sg
+            out[f"pod/{nm}/v{variant}/t{st}/absW"] = np.abs(Wm)
     for nm, D in pca_inputs().items():
         if nm in ("tourists", "athletic"):
             out[f"pca/{nm}/data"] = D

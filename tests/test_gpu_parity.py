@@ -689,3 +689,103 @@ def test_cpp_pca_header(oracle, tmp_path):
         assert "invalid_argument: PCA requires at least 2 rows and 2 columns." in out
         txt = (tmp_path / f"o{norm}_results.txt").read_text()
         assert "Cumulative Explained Variance:" in txt and "Scores:" in txt and "Loadings:" in txt
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# POD wrappers (POD/ParametricDiffusion1D/src/POD.cpp) on the device
+# ---------------------------------------------------------------------------------------------------------------------
+def _pod_compare(Wm, sg, absW_ref, sg_ref, r, loose):
+    tol = 1e-6 if loose else 1e-8
+    assert sg.shape == sg_ref.shape and Wm.shape == absW_ref.shape          # same N from the energy criterion
+    assert np.max(np.abs(sg[:r] - sg_ref[:r])) <= tol * sg_ref[0]
+    s = sg_ref[:Wm.shape[1]]
+    ok = s > 1e-9 * sg_ref[0]
+    d = np.abs(np.diff(sg_ref[:Wm.shape[1] + 1])) if len(sg_ref) > len(s) else np.r_[np.abs(np.diff(s)), np.inf]
+    ok &= d[: len(s)] > 1e-4 * sg_ref[0]
+    ok[1:] &= np.abs(np.diff(s)) > 1e-4 * sg_ref[0]
+    if ok.any():
+        scale = np.abs(absW_ref[:, ok]).max()
+        assert np.max(np.abs(np.abs(Wm[:, ok]) - absW_ref[:, ok])) <= (1e-3 if loose else 1e-6) * scale
+
+
+@pytest.mark.parametrize("name", list(G.pod_inputs().keys()))
+def test_pod_vs_oracle_and_reference_golden(engine, oracle, name):
+    from rsvd_kamaneh_raganato_terrana_b200 import POD
+    g = np.load(Path(__file__).resolve().parent / "golden" / "ref_outputs.npz")
+    S, Xh, D, r, tol = G.pod_inputs()[name]
+    for variant, st in G.POD_CASES:
+        key = f"pod/{name}/v{variant}/t{st}/"
+        if key + "sigma" not in g.files:
+            continue
+        Om = G.pod_omega(S, variant, r) if st >= 3 else None
+        args = {0: (r, st), 1: (r, tol, st), 2: (Xh, r, tol, st), 3: (Xh, D, r, tol, st)}[variant]
+        p = POD(engine, S, *args, Omega=Om)
+        # ParallelJacobi stops early in the reference (1e-7..1e-4 floors); ours converges fully
+        _pod_compare(p.W, p.sigma, g[key + "absW"], g[key + "sigma"], r, loose=st in (2, 5))
+        Wo, so = oracle.pod(variant, S, r, tol, 1 if st == 2 else (4 if st == 5 else st), Xh if variant >= 2 else None, D if variant == 3 else None, Om)
+        _pod_compare(p.W, p.sigma, np.abs(Wo), so, r, loose=False)
+        if variant == 1 and S.shape[1] <= S.shape[0]:
+            # modes of the correlation-matrix route span the leading left singular subspace of S (scaled by 1/sigma(S), the
+            # reference's division by sigma(C) = sigma(S)^2)
+            Us = np.linalg.svd(S, full_matrices=False)[0][:, :p.W.shape[1]]
+            Wn = p.W / np.linalg.norm(p.W, axis=0)
+            assert oracle.subspace_sin_theta(Us, Wn) < 1e-5
+
+
+def test_pod_power_backends_and_errors(engine, oracle):
+    """svd_type 0 / 3 (Power back-ends; random start vectors -> compared through sigma and the energy criterion only)"""
+    from rsvd_kamaneh_raganato_terrana_b200 import POD
+    S, Xh, D, r, tol = G.pod_inputs()["decay_300x40"]
+    r = 6
+    for variant, args in ((0, (r,)), (1, (r, tol))):
+        for st in (0, 3):
+            p = POD(engine, S, *args, st, Omega=G.pod_omega(S, variant, r) if st == 3 else None)
+            Wo, so = oracle.pod(variant, S, r, tol, st, Omega=G.pod_omega(S, variant, r) if st == 3 else None)
+            assert p.W.shape == Wo.shape and p.sigma.shape == so.shape
+            assert np.max(np.abs(p.sigma[:r] - so[:r])) <= 1e-6 * so[0]
+    with pytest.raises(ValueError, match=r"svd_type should be in \[0,5\]"):
+        POD(engine, S, 4, 1e-2, 9)
+    with pytest.raises(ValueError):
+        POD(engine, S, 400, 1e-2, 1)          # r larger than the correlation matrix
+
+
+def test_pod_config4_shape_on_device(engine, oracle):
+    """config-4-shaped snapshots (scaled to 20000 x 1000): standard POD with the rSVD back-end, all on the device"""
+    import torch
+    Nh, ns, r = 20000, 1000, 32
+    S = W.c4_pod(Nh, ns)
+    dev = torch.device("cuda:0")
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    Sd = torch.from_numpy(np.ascontiguousarray(S.T)).to(dev)
+    Om = W.omega(ns, r); Od = torch.from_numpy(np.ascontiguousarray(Om.T)).to(dev)
+    Wd = torch.empty((r, Nh), dtype=torch.float64, device=dev); sg = torch.empty(r, dtype=torch.float64, device=dev)
+    import ctypes
+    N = ctypes.c_int()
+    engine._check(engine.lib.rsvdb_pod_dev(engine.h, 1, Sd.data_ptr(), Nh, ns, Nh, None, 0, None, 0, r, 1e-4, 4, 0, Od.data_ptr(), ns,
+                                           Wd.data_ptr(), Nh, sg.data_ptr(), ctypes.byref(N)))
+    torch.cuda.synchronize()
+    engine.lib.rsvdb_use_own_stream(engine.h)
+    Wo, so = oracle.pod(1, S, r, 1e-4, 4, Omega=Om)
+    assert N.value == Wo.shape[1]
+    assert oracle.sigma_close(sg.cpu().numpy(), so)[0]
+    sv = np.linalg.svd(S, compute_uv=False)
+    assert np.max(np.abs(np.sqrt(sg.cpu().numpy()[:N.value]) - sv[:N.value])) <= 1e-6 * sv[0]      # sigma(C) = sigma(S)^2
+
+
+def test_cpp_pod_header(oracle, tmp_path):
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "pod_test"; libdir = root / "rsvd_kamaneh_raganato_terrana_b200"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-I", str(root / "include"), "-o", str(exe), str(root / "tests" / "cpp" / "pod_test.cpp"),
+                    "-L", str(libdir), "-lrsvdb", f"-Wl,-rpath,{libdir}"], check=True)
+    S, Xh, D, r, tol = G.pod_inputs()["decay_300x40"]
+    Nh, ns = S.shape
+    S.ravel(order="F").tofile(tmp_path / "S.bin")
+    out = subprocess.run([str(exe), str(tmp_path / "S.bin"), str(Nh), str(ns), str(r), str(tol), "1", str(tmp_path / "o")], check=True,
+                         capture_output=True, text=True).stdout
+    g = np.load(Path(__file__).resolve().parent / "golden" / "ref_outputs.npz")
+    for tag, variant in (("naive", 0), ("std", 1), ("energy", 2), ("weight", 3)):
+        sg = np.fromfile(tmp_path / f"o_{tag}_sigma.bin"); ref_abs = g[f"pod/decay_300x40/v{variant}/t1/absW"]
+        Wm = np.fromfile(tmp_path / f"o_{tag}_W.bin").reshape((Nh, -1), order="F")
+        _pod_compare(Wm, sg, ref_abs, g[f"pod/decay_300x40/v{variant}/t1/sigma"], r, loose=False)
+    assert f"naive W {Nh} x {ns} sigma {ns}" in out

@@ -162,3 +162,37 @@ def test_pca_rejects_degenerate_input(oracle):
     if oracle.RefLib.available():
         with pytest.raises(ValueError, match="at least 2 rows and 2 columns"):
             oracle.RefLib().pca(np.zeros((5, 1)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# POD wrappers: the numpy restatement vs the reference's own POD class (golden)
+# ---------------------------------------------------------------------------------------------------------------------
+def _pod_compare(Wm, sg, absW_ref, sg_ref, r, loose):
+    tol = 1e-6 if loose else 1e-9
+    assert sg.shape == sg_ref.shape and Wm.shape == absW_ref.shape          # same N from the energy criterion
+    assert np.max(np.abs(sg[:r] - sg_ref[:r])) <= tol * sg_ref[0]
+    # modes agree up to sign where the singular values are separated and not at noise level
+    s = sg_ref[:Wm.shape[1]]
+    gap = np.r_[np.abs(np.diff(sg_ref[:Wm.shape[1] + 1]))[: len(s)], np.inf][: len(s)] if len(sg_ref) > len(s) else np.r_[np.abs(np.diff(s)), np.inf]
+    ok = (gap > 1e-4 * sg_ref[0]) & (s > 1e-9 * sg_ref[0])
+    ok[1:] &= np.abs(np.diff(s)) > 1e-4 * sg_ref[0]
+    if ok.any():
+        scale = np.abs(absW_ref[:, ok]).max()
+        assert np.max(np.abs(np.abs(Wm[:, ok]) - absW_ref[:, ok])) <= (1e-3 if loose else 1e-6) * scale
+
+
+@pytest.mark.parametrize("name", list(G.pod_inputs().keys()))
+def test_pod_restatement_matches_reference_class(oracle, name):
+    S, Xh, D, r, tol = G.pod_inputs()[name]
+    for variant, st in G.POD_CASES:
+        key = f"pod/{name}/v{variant}/t{st}/"
+        if key + "sigma" not in GOLD.files:
+            continue
+        Wm, sg = oracle.pod(variant, S, r, tol, st, Xh if variant >= 2 else None, D if variant == 3 else None,
+                            G.pod_omega(S, variant, r) if st >= 3 else None)
+        _pod_compare(Wm, sg, GOLD[key + "absW"], GOLD[key + "sigma"], r, loose=st in (2, 5))
+
+
+def test_pod_bad_svd_type(oracle):
+    with pytest.raises(ValueError, match=r"svd_type should be in \[0,5\]"):
+        oracle.pod(1, np.eye(6), 2, 1e-3, 7)
