@@ -202,6 +202,27 @@ RSVDB_API int rsvdb_pod_dev(rsvdb_ctx* ctx, int variant, const double* dS, int64
                             int64_t ldx, const double* dD, int64_t ldd, int r, double tol, int svd_type, uint64_t seed,
                             const double* dOmega, int64_t ldo, double* dW, int64_t ldw, double* d_sigma, int* N);
 
+/* ---- Image::compress-shaped driver ----------------------------------------------------------------
+ * Reference: image_compression/src/image_com.cpp.  image is m x n column-major (Image::image_matrix). */
+
+/* Image::normalize() (:251-264) + Image::compress(k) (:288-317): min-max normalisation to [0,1] when normalize != 0 (skipped
+ * with a warning in the reference when min >= max; here *original_min / *original_max report the range either way), then the
+ * older-API rSVD(A, U, S, V, l) (image_compression/src/rSVD.cpp:77-118: q = 1, power-method back-end) with l = k + 10
+ * (k = -1: min(m, n) / 4).  Outputs U m x l, S l, V n x l (columns), *degree = l.  Omega (n x l) optional. */
+RSVDB_API int rsvdb_image_compress_host(rsvdb_ctx* ctx, const double* image, int64_t m, int64_t n, int64_t ld, int k, int normalize,
+                                        const double* Omega, int64_t ldo, uint64_t seed, double* original_min, double* original_max,
+                                        double* U, int64_t ldu, double* S, double* V, int64_t ldv, int* degree);
+/* Image::normalize() (inverse == 0, :251-264: finds min / max, writes them to *original_min / *original_max and maps the
+ * image to [0,1] in place) or Image::deNormalize() (inverse != 0, :270-281: uses the given range).  A no-op on the data when
+ * min >= max (the reference prints a warning); returns RSVDB_OK either way. */
+RSVDB_API int rsvdb_image_normalize_host(rsvdb_ctx* ctx, double* image, int64_t m, int64_t n, int64_t ld, int inverse,
+                                         double* original_min, double* original_max);
+/* Image::reconstruct() (:184-190) + Image::deNormalize() (:270-281): out (m x n) = U diag(S) V^T, then x * (max - min) + min when
+ * denormalize != 0 and min < max -- the affine map is applied in the same pass over the result. */
+RSVDB_API int rsvdb_image_reconstruct_host(rsvdb_ctx* ctx, const double* U, int64_t m, int64_t ldu, const double* S, const double* V,
+                                           int64_t n, int64_t ldv, int l, int denormalize, double original_min, double original_max,
+                                           double* out, int64_t ldout);
+
 /* Number of power iterations PM runs for an n-column matrix (src/PM.cpp:25-28). */
 RSVDB_API int rsvdb_pm_iterations(int64_t ncols);
 

@@ -14,6 +14,9 @@ What is restated (reference file:line, relative to /root/reference):
 * ``pod``                POD/ParametricDiffusion1D/src/POD.cpp:42-114 (perform_SVD), :116-134 (naive), :136-224
                          (standard), :226-336 (energy), :338-461 (weight); Eigen's SelfAdjointEigenSolver::operatorSqrt
                          and ConjugateGradient are restated through numpy eigh / solve
+* ``image_*``            image_compression/src/image_com.cpp:184-190,251-317 (normalise, compress = older-API rSVD with
+                         l = k + 10, reconstruct, deNormalize); NOT compiled from the reference (its Image class is only
+                         reachable through the stb PNG codec): "parity unpinned" for this wrapper, the pieces are pinned above
 * ``PCA``                PCA/include/PCA_class.hpp:24-47 (centre, optional stddev scaling, SVD<method>), :76-100
                          (explained variance / ratio, scores, loadings, projectToPCA, reconstructFromPCA)
 
@@ -162,6 +165,38 @@ def rsvd(A, Omega, l: int, q: int = 2, method: int = JACOBI, seed: int = 0):
     else:
         raise ValueError("Unsupported SVD method")   # std::invalid_argument, :122-123
     return Q @ Ut, S, V                          # :128
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Image::normalize / compress / reconstruct / deNormalize (image_compression/src/image_com.cpp)
+# ---------------------------------------------------------------------------------------------------------------
+def image_normalize(A):
+    """image_com.cpp:251-264.  Returns (normalised image, min, max); unchanged when min >= max."""
+    A = np.asarray(A, dtype=np.float64); lo, hi = float(A.min()), float(A.max())
+    return ((A - lo) / (hi - lo) if lo < hi else A.copy()), lo, hi
+
+
+def image_denormalize(A, lo, hi):
+    """image_com.cpp:270-281."""
+    return A * (hi - lo) + lo if lo < hi else np.array(A, dtype=np.float64)
+
+
+def image_compress(A, k: int = -1, Omega=None, seed: int = 0):
+    """image_com.cpp:288-317: l = k + 10, older-API rSVD (image_compression/src/rSVD.cpp:77-118: q = 1, power-method SVD of B).
+    Returns (U m x l, S l, V n x l)."""
+    A = np.asarray(A, dtype=np.float64); m, n = A.shape
+    if k == -1:
+        k = min(m, n) // 4
+    l = k + 10
+    if Omega is None:
+        Omega = np.random.default_rng(seed).standard_normal((n, l))
+    U, S, Vrows = rsvd(A, Omega, l, 1, POWER, seed)
+    return U, S, np.asfortranarray(Vrows[:l, :].T)          # the older API returns V with the vectors in columns
+
+
+def image_reconstruct(U, S, V):
+    """image_com.cpp:184-190."""
+    return (U * S) @ V.T
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -5,4 +5,4 @@ script, the ctypes binding and a Python mirror of the reference's operator inter
 load the library; the first use does, and fails loudly if it has not been built.
 """
 from .capi import RsvdbError  # noqa: F401
-from .engine import Engine, PCA, POD, SVD, SVDMethod, rSVD, intermediate_step, generateOmega  # noqa: F401
+from .engine import Engine, Image, PCA, POD, SVD, SVDMethod, rSVD, intermediate_step, generateOmega  # noqa: F401

@@ -83,6 +83,10 @@ def _declare(lib):
         "rsvdb_pod_shape": [c_int, i64, i64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)],
         "rsvdb_pod_host": [vp, c_int, vp, i64, i64, i64, vp, i64, vp, i64, c_int, c_double, c_int, u64, vp, i64, vp, i64, vp, POINTER(c_int)],
         "rsvdb_pod_dev": [vp, c_int, vp, i64, i64, i64, vp, i64, vp, i64, c_int, c_double, c_int, u64, vp, i64, vp, i64, vp, POINTER(c_int)],
+        "rsvdb_image_compress_host": [vp, vp, i64, i64, i64, c_int, c_int, vp, i64, u64, POINTER(c_double), POINTER(c_double), vp, i64, vp, vp, i64,
+                                      POINTER(c_int)],
+        "rsvdb_image_normalize_host": [vp, vp, i64, i64, i64, c_int, POINTER(c_double), POINTER(c_double)],
+        "rsvdb_image_reconstruct_host": [vp, vp, i64, i64, vp, vp, i64, i64, c_int, c_int, c_double, c_double, vp, i64],
         "rsvdb_qr_host": [vp, vp, i64, i64, i64, c_int, vp, i64, vp, i64],
         "rsvdb_pm_host": [vp, vp, i64, i64, i64, u64, POINTER(c_double), vp, vp],
         "rsvdb_gemm_host": [vp, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64],

@@ -6,6 +6,7 @@
 
 #include "comm.cuh"
 #include "context.cuh"
+#include "image.cuh"
 #include "pca.cuh"
 #include "pipeline.cuh"
 #include "pod.cuh"
@@ -533,6 +534,84 @@ int rsvdb_pod_host(rsvdb_ctx* c, int variant, const double* S, int64_t Nh, int64
   RSVDB_TRY(pod_device(c, variant, dS, Nh, ns, ldS, dX, ldS, dD, ldD, r, tol, svd_type, seed, dOm, ldOm, dW, ldS, dSig, N));
   RSVDB_TRY(d2h(c, W, ldw, dW, ldS, Nh, *N));             // the basis after conservativeResize(NoChange, N), POD.cpp:221
   RSVDB_TRY(d2h(c, sigma, sh.sigma_len, dSig, sh.sigma_len, sh.sigma_len, 1));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_image_compress_host(rsvdb_ctx* c, const double* image, int64_t m, int64_t n, int64_t ld, int k, int normalize, const double* Omega,
+                              int64_t ldo, uint64_t seed, double* original_min, double* original_max, double* U, int64_t ldu, double* S,
+                              double* V, int64_t ldv, int* degree) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (!image || !U || !S || !V || m <= 0 || n <= 0 || ld < m || ldu < m || ldv < n) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "Image::compress: bad argument");
+  if (k == -1) k = (int)(std::min(m, n) / 4);                       // image_com.cpp:293-295
+  const int l = k + 10;                                             // oversampling p = 10, :297-298
+  if (k < 0 || l > n || (Omega && ldo < n)) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "Image::compress: k + 10 must not exceed the image width");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t ldA = even_ld(m), ldO = even_ld(n);
+  const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)ldO * l) + IoArena::pad((size_t)ldA * l) +
+                       IoArena::pad((size_t)ldO * l) + IoArena::pad((size_t)l) + IoArena::pad(8)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  double* dA = ar.take((size_t)ldA * n); double* dO = ar.take((size_t)ldO * l); double* dU = ar.take((size_t)ldA * l);
+  double* dV = ar.take((size_t)ldO * l); double* dS = ar.take((size_t)l); double* dmm = ar.take(8);
+  RSVDB_TRY(h2d(c, dA, ldA, image, ld, m, n));
+  if (Omega) { RSVDB_TRY(h2d(c, dO, ldO, Omega, ldo, n, l)); }
+  else { RSVDB_TRY(rsvdb_generate_omega_dev(c, n, l, seed, dO, ldO)); }
+  RSVDB_TRY(image_minmax(c, dA, m, n, ldA, dmm));
+  if (normalize) RSVDB_TRY(image_affine(c, dA, m, n, ldA, dmm, false));
+  RSVDB_TRY(rsvd_device(c, dA, m, n, ldA, dO, ldO, l, /*q=*/1, RSVDB_SVD_POWER, dU, ldA, dS, dV, ldO, seed));
+  double mm[2] = {0.0, 0.0};
+  RSVDB_TRY(d2h(c, mm, 2, dmm, 2, 2, 1));
+  RSVDB_TRY(d2h(c, U, ldu, dU, ldA, m, l));
+  RSVDB_TRY(d2h(c, S, l, dS, l, l, 1));
+  RSVDB_TRY(d2h(c, V, ldv, dV, ldO, n, l));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (original_min) *original_min = mm[0];
+  if (original_max) *original_max = mm[1];
+  if (degree) *degree = l;
+  return RSVDB_OK;
+}
+
+int rsvdb_image_normalize_host(rsvdb_ctx* c, double* image, int64_t m, int64_t n, int64_t ld, int inverse, double* original_min,
+                               double* original_max) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (!image || !original_min || !original_max || m <= 0 || n <= 0 || ld < m) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "Image::normalize: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t ldA = even_ld(m);
+  RSVDB_CUDA(c, c->io_ws.reserve((IoArena::pad((size_t)ldA * n) + IoArena::pad(8)) * 8 + 256));
+  IoArena ar(c);
+  double* dA = ar.take((size_t)ldA * n); double* dmm = ar.take(8);
+  RSVDB_TRY(h2d(c, dA, ldA, image, ld, m, n));
+  double mm[2] = {*original_min, *original_max};
+  if (inverse) { RSVDB_TRY(h2d(c, dmm, 2, mm, 2, 2, 1)); }
+  else { RSVDB_TRY(image_minmax(c, dA, m, n, ldA, dmm)); RSVDB_TRY(d2h(c, mm, 2, dmm, 2, 2, 1)); }
+  RSVDB_TRY(image_affine(c, dA, m, n, ldA, dmm, inverse != 0));
+  RSVDB_TRY(d2h(c, image, ld, dA, ldA, m, n));
+  RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *original_min = mm[0]; *original_max = mm[1];
+  return RSVDB_OK;
+}
+
+int rsvdb_image_reconstruct_host(rsvdb_ctx* c, const double* U, int64_t m, int64_t ldu, const double* S, const double* V, int64_t n, int64_t ldv,
+                                 int l, int denormalize, double original_min, double original_max, double* out, int64_t ldout) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (!U || !S || !V || !out || m <= 0 || n <= 0 || l <= 0 || ldu < m || ldv < n || ldout < m || n > INT32_MAX)
+    return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "Image::reconstruct: bad argument");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const int64_t ldA = even_ld(m), ldO = even_ld(n);
+  const size_t need = (IoArena::pad((size_t)ldA * n) + IoArena::pad((size_t)ldA * l) + IoArena::pad((size_t)ldO * l) + IoArena::pad((size_t)l) +
+                       IoArena::pad(8)) * 8 + 256;
+  RSVDB_CUDA(c, c->io_ws.reserve(need));
+  IoArena ar(c);
+  double* dOut = ar.take((size_t)ldA * n); double* dU = ar.take((size_t)ldA * l); double* dV = ar.take((size_t)ldO * l);
+  double* dS = ar.take((size_t)l); double* dmm = ar.take(8);
+  RSVDB_TRY(h2d(c, dU, ldA, U, ldu, m, l));
+  RSVDB_TRY(h2d(c, dV, ldO, V, ldv, n, l));
+  RSVDB_TRY(h2d(c, dS, l, S, l, l, 1));
+  const double mm[2] = {original_min, original_max};
+  if (denormalize) RSVDB_TRY(h2d(c, dmm, 2, mm, 2, 2, 1));
+  RSVDB_TRY(image_reconstruct(c, dU, m, ldA, dS, dV, n, ldO, l, denormalize ? dmm : nullptr, dOut, ldA));
+  RSVDB_TRY(d2h(c, out, ldout, dOut, ldA, m, n));
   RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RSVDB_OK;
 }

@@ -308,6 +308,39 @@ class Engine:
         return np.asfortranarray(W[:, :N.value]), sigma
 
 
+    # -- Image::compress-shaped driver (image_compression/src/image_com.cpp) --------------------------------------------
+    def image_compress(self, image, k: int = -1, normalize: bool = True, Omega=None, seed: int = 0):
+        """Image::normalize + Image::compress in one upload -- image_com.cpp:251-264,288-317.  Returns (U, S, V, min, max, l)."""
+        A = _f(image); m, n = A.shape
+        kk = min(m, n) // 4 if k == -1 else k
+        l = kk + 10
+        if l > n or kk < 0:
+            raise ValueError("Image::compress: k + 10 must not exceed the image width")
+        U = np.zeros((m, l), order="F"); S = np.zeros(l); V = np.zeros((n, l), order="F")
+        lo = ctypes.c_double(); hi = ctypes.c_double(); deg = ctypes.c_int()
+        om_ptr, ldo = None, 0
+        if Omega is not None:
+            Omega = _f(Omega); om_ptr, ldo = _ptr(Omega), n
+        self._check(self.lib.rsvdb_image_compress_host(self.h, _ptr(A), m, n, m, int(k), int(bool(normalize)), om_ptr, ldo, seed, ctypes.byref(lo),
+                                                       ctypes.byref(hi), _ptr(U), m, _ptr(S), _ptr(V), n, ctypes.byref(deg)))
+        return U, S, V, lo.value, hi.value, deg.value
+
+    def image_normalize(self, image, inverse: bool = False, lo: float = 0.0, hi: float = 0.0):
+        """Image::normalize / deNormalize -- image_com.cpp:251-281.  Returns (mapped image, min, max)."""
+        A = _f(image).copy(order="F"); m, n = A.shape
+        clo = ctypes.c_double(lo); chi = ctypes.c_double(hi)
+        self._check(self.lib.rsvdb_image_normalize_host(self.h, _ptr(A), m, n, m, int(bool(inverse)), ctypes.byref(clo), ctypes.byref(chi)))
+        return A, clo.value, chi.value
+
+    def image_reconstruct(self, U, S, V, denormalize: bool = False, lo: float = 0.0, hi: float = 1.0):
+        """Image::reconstruct (+ deNormalize in the same pass) -- image_com.cpp:184-190,270-281."""
+        U = _f(U); V = _f(V); S = np.ascontiguousarray(S, dtype=np.float64); m, l = U.shape; n = V.shape[0]
+        out = np.zeros((m, n), order="F")
+        self._check(self.lib.rsvdb_image_reconstruct_host(self.h, _ptr(U), m, m, _ptr(S), _ptr(V), n, n, l, int(bool(denormalize)), float(lo), float(hi),
+                                                          _ptr(out), m))
+        return out
+
+
 def _power_v_layout(Vcols: np.ndarray, n: int, dim: int, found: int) -> np.ndarray:
     """The Power back-end stores right singular vectors in the ROWS of an identity-initialised n x n matrix
     (include/SVD_class.hpp:83,214)."""
@@ -414,6 +447,58 @@ class PCA(SVD):
                 f.write(f"\n{title}:\n")
                 for row in M:
                     f.write(", ".join(f"{x:g}" for x in row) + "\n")
+
+
+class Image:
+    """class Image -- image_compression/include/image_comp.hpp:16-118, minus the stb codec (load / save), which is out of
+    scope: the pixel matrix comes in through setMatrix.  normalize / compress / reconstruct / deNormalize run on the device."""
+
+    def __init__(self, engine: Engine, width: int = 0, height: int = 0):
+        self._e = engine
+        self.originalWidth, self.originalHeight = width, height
+        self.image_matrix = None
+        self.left_singular = self.singular = self.right_singular = None
+        self.original_min = self.original_max = 0.0
+        self.degree = 0
+
+    def setMatrix(self, M):                                   # additive (the reference fills image_matrix in load(), :18-44)
+        self.image_matrix = _f(M).copy(order="F")
+        self.originalHeight, self.originalWidth = self.image_matrix.shape[1], self.image_matrix.shape[0]   # load() stores the transpose
+
+    def getMatrix(self):
+        return self.image_matrix.copy(order="F")
+
+    def normalize(self):                                      # :251-264
+        self.image_matrix, self.original_min, self.original_max = self._e.image_normalize(self.image_matrix)
+
+    def deNormalize(self):                                    # :270-281
+        self.image_matrix, _, _ = self._e.image_normalize(self.image_matrix, True, self.original_min, self.original_max)
+
+    def compress(self, k: int = -1, Omega=None, seed: int = 0):   # :288-317
+        U, S, V, _, _, l = self._e.image_compress(self.image_matrix, k, False, Omega, seed)
+        self.left_singular, self.singular, self.right_singular, self.degree = U, S, V, l
+
+    def normalize_and_compress(self, k: int = -1, Omega=None, seed: int = 0):
+        """additive: normalize() + compress(k) with ONE upload; image_matrix itself is left untouched"""
+        U, S, V, self.original_min, self.original_max, l = self._e.image_compress(self.image_matrix, k, True, Omega, seed)
+        self.left_singular, self.singular, self.right_singular, self.degree = U, S, V, l
+
+    def reconstruct(self, denormalize: bool = False):         # :184-190 (denormalize: additive, fused deNormalize)
+        return self._e.image_reconstruct(self.left_singular, self.singular, self.right_singular, denormalize, self.original_min, self.original_max)
+
+    def downscale(self, scale_factor: int = -1):              # :193-217 (index shuffles on the host, like the reference)
+        f = 2 if scale_factor == -1 else scale_factor
+        nw, nh = self.originalWidth // f, self.originalHeight // f
+        self.image_matrix = np.asfortranarray(self.image_matrix[: nh * f: f, : nw * f: f][:nh, :nw])
+        self.originalWidth, self.originalHeight = nw, nh
+
+    def upscale(self, scale_factor: int = -1):                # :219-244
+        f = 2 if scale_factor == -1 else scale_factor
+        self.image_matrix = np.asfortranarray(np.kron(self.image_matrix[: self.originalHeight, : self.originalWidth], np.ones((f, f))))
+        self.originalWidth, self.originalHeight = self.originalWidth * f, self.originalHeight * f
+
+    def get_compression_ratio(self) -> float:                 # :406-411
+        return (self.originalHeight * self.originalWidth) / (self.degree * (self.originalWidth + self.originalHeight + 1))
 
 
 class POD:

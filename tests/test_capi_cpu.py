@@ -59,10 +59,10 @@ def test_cpp_dropin_headers_compile_and_link():
     libdir = ROOT / "rsvd_kamaneh_raganato_terrana_b200"
     out = ROOT / "build"
     out.mkdir(exist_ok=True)
-    for src in ("rsvd_dropin_test.cpp", "rsvd_test_main.cpp", "rsvd_v1_test.cpp", "pca_test.cpp", "pod_test.cpp"):
+    for src in ("rsvd_dropin_test.cpp", "rsvd_test_main.cpp", "rsvd_v1_test.cpp", "pca_test.cpp", "pod_test.cpp", "image_test.cpp"):
         subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-o", str(out / (src[:-4] + "_cpu")),
                         str(ROOT / "tests" / "cpp" / src), "-L", str(libdir), "-lrsvdb", f"-Wl,-rpath,{libdir}"], check=True)
     # every reference header name on the path has a drop-in of the same name
     for h in ("rSVD.hpp", "SVD_class.hpp", "QR.hpp", "PM.hpp", "Jacobi_Class.hpp", "JacobiOperations.hpp", "matrixOperations.hpp", "PCA_class.hpp", "POD.hpp",
-              "image_compression/rSVD.hpp", "image_compression/SVD.hpp", "image_compression/PowerMethod.hpp", "image_compression/QR.hpp"):
+              "image_compression/rSVD.hpp", "image_compression/SVD.hpp", "image_compression/PowerMethod.hpp", "image_compression/QR.hpp", "image_compression/image_comp.hpp"):
         assert (ROOT / "include" / h).exists(), h

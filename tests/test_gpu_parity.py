@@ -789,3 +789,78 @@ def test_cpp_pod_header(oracle, tmp_path):
         Wm = np.fromfile(tmp_path / f"o_{tag}_W.bin").reshape((Nh, -1), order="F")
         _pod_compare(Wm, sg, ref_abs, g[f"pod/decay_300x40/v{variant}/t1/sigma"], r, loose=False)
     assert f"naive W {Nh} x {ns} sigma {ns}" in out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the Image::normalize / compress / reconstruct / deNormalize driver (image_com.cpp)
+# ---------------------------------------------------------------------------------------------------------------------
+def _small_image(m=512, n=384, seed=2):
+    A = W.c2_image(max(m, n), seed)[:m, :n]
+    return np.asfortranarray(np.round(A * 255.0))   # pixel values like a decoded 8-bit picture
+
+
+def test_image_compress_driver_vs_oracle(engine, oracle):
+    from rsvd_kamaneh_raganato_terrana_b200 import Image
+    A = _small_image()
+    m, n = A.shape; k = 20; l = k + 10
+    Om = W.omega(n, l)
+    U, S, V, lo, hi, deg = engine.image_compress(A, k, True, Om)
+    An, olo, ohi = oracle.image_normalize(A)
+    assert (lo, hi, deg) == (olo, ohi, l)
+    Uo, So, Vo = oracle.image_compress(An, k, Om)
+    assert U.shape == Uo.shape == (m, l) and V.shape == Vo.shape == (n, l)
+    # power-method back-end: 148 iterations from a random start (std::random_device in the reference) resolve a singular value
+    # only as far as its gap allows -- well-separated leading values agree to rounding, the clustered tail to ~(s_{i+1}/s_i)^296
+    sep = np.r_[So[1:] / So[:-1] < 0.5, False]
+    assert sep[:2].all() and np.max(np.abs(S[sep] - So[sep]) / So[sep]) <= 1e-9
+    assert np.max(np.abs(S - So) / So) <= 2e-2 and abs((S ** 2).sum() - (So ** 2).sum()) <= 1e-4 * (So ** 2).sum()
+    rec = engine.image_reconstruct(U, S, V)
+    assert abs(np.linalg.norm(An - rec) - np.linalg.norm(An - oracle.image_reconstruct(Uo, So, Vo))) <= 1e-3 * np.linalg.norm(An)
+    np.testing.assert_allclose(rec, (U * S) @ V.T, rtol=0, atol=1e-12 * np.abs(rec).max())
+    den = engine.image_reconstruct(U, S, V, True, lo, hi)
+    np.testing.assert_allclose(den, oracle.image_denormalize(rec, lo, hi), rtol=0, atol=1e-12 * np.abs(den).max())
+    # the class, step by step like image_compression/main/main.cpp:44-80
+    img = Image(engine); img.setMatrix(A[:n, :n])          # downscale / upscale are only well defined for square pictures in the reference
+    img.downscale(2)
+    np.testing.assert_array_equal(img.getMatrix(), A[:n:2, :n:2])
+    img.upscale(2)
+    assert img.getMatrix().shape == (n, n) and np.array_equal(img.getMatrix()[1::2, 1::2], A[:n:2, :n:2])
+    img.setMatrix(A); img.normalize()
+    np.testing.assert_array_equal(img.getMatrix(), An)                            # same IEEE operations, same bits
+    img.compress(k, Omega=Om)
+    assert img.degree == l and np.max(np.abs(img.singular - So) / So) <= 2e-2
+    img.deNormalize()
+    np.testing.assert_allclose(img.getMatrix(), A, rtol=0, atol=1e-12 * np.abs(A).max())
+    assert abs(img.get_compression_ratio() - (m * n) / (l * (m + n + 1))) < 1e-12
+    img2 = Image(engine); img2.setMatrix(A); img2.normalize_and_compress(k, Omega=Om)
+    np.testing.assert_array_equal(img2.singular, S)
+    # constant image: the range is empty, normalisation is skipped (image_com.cpp:261-263)
+    flat = np.full((64, 48), 7.0); fn, flo, fhi = engine.image_normalize(flat)
+    assert (flo, fhi) == (7.0, 7.0) and np.array_equal(fn, flat)
+    with pytest.raises(ValueError):
+        engine.image_compress(A, n)                                               # k + 10 > width
+
+
+def test_cpp_image_header(oracle, tmp_path):
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "image_test"; libdir = root / "rsvd_kamaneh_raganato_terrana_b200"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-I", str(root / "include"), "-o", str(exe), str(root / "tests" / "cpp" / "image_test.cpp"),
+                    "-L", str(libdir), "-lrsvdb", f"-Wl,-rpath,{libdir}"], check=True)
+    A = _small_image(256, 256); m, n = A.shape; k = 12
+    A.ravel(order="F").tofile(tmp_path / "A.bin")
+    out = subprocess.run([str(exe), str(tmp_path / "A.bin"), str(m), str(n), str(k), str(tmp_path / "o")], check=True, capture_output=True, text=True).stdout
+    rd = lambda name, shape: np.fromfile(tmp_path / f"o_{name}.bin").reshape(shape, order="F")
+    D = A[::2, ::2]                                                               # downscale(2), image_com.cpp:193-217
+    Dn, lo, hi = oracle.image_normalize(D)
+    np.testing.assert_array_equal(rd("normalized", D.shape), Dn)
+    assert f"range {lo:.17g} {hi:.17g}" in out
+    S = rd("S", (k + 10,)); sv = np.linalg.svd(Dn, compute_uv=False)
+    assert np.all(S[:k] <= sv[:k] * (1 + 1e-9)) and np.all(S[:k] >= 0.9 * sv[:k]) and abs(S[0] - sv[0]) <= 1e-6 * sv[0]   # q = 1 sketch of a noisy picture: lower bounds
+    rec = rd("rec", D.shape)
+    assert np.linalg.norm(Dn - rec) <= 2.0 * np.sqrt((sv[k:] ** 2).sum()) + 1e-9
+    np.testing.assert_allclose(rd("rec_denorm", D.shape), rec * (hi - lo) + lo, rtol=0, atol=1e-10 * hi)
+    fin = rd("final", (m, n))
+    assert np.linalg.norm(fin[::2, ::2] - D) <= 2.0 * np.sqrt((sv[k:] ** 2).sum()) * (hi - lo) + 1e-6
+    assert np.array_equal(fin[::2, ::2], fin[1::2, 1::2])                          # upscale(2) repeats pixels
+    assert f"final {m} x {n}" in out and f"compressed file: U {m // 2} x {k + 10}" in out
