@@ -333,154 +333,6 @@ __device__ __forceinline__ void block_reflect(double* S, const double* Vp, const
   }
 }
 
-template <int N> __device__ __forceinline__ void warp_sum_n(double (&v)[N]) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-  }
-}
-
-// All 8 warps factor the panel of pb (<= 8) columns starting at column / diagonal row c0: thread (warp, lane) owns row
-// 32*warp + lane of the panel in registers.  Per reflector there is ONE fused reduction (the column's tail norm and its
-// inner products with the remaining panel columns travel together: warp shuffles, then 8 partials per value through
-// shared memory, double-buffered so that one block barrier per reflector suffices).  The Gram matrix V^T V needed for T
-// (LAPACK dlarft, forward / columnwise) is formed on the tensor cores.
-// Outputs: S panel columns in storage form (R above the diagonal, beta on it, scaled reflectors below), the clean
-// reflectors in Vp (unit diagonal, zeros above, zero columns past pb), T (8x8 column-major, zero-padded), tau.
-// scratch: 2*64 (partials) + 2*8 (diagonal row) + 8*64 (Gram partials) + 64 (Gram) doubles.
-template <int BR>
-__device__ __forceinline__ void panel_factor(double* S, double* Vp, double* Tsm, double* tau_s, double* Tglob, double* scratch,
-                                             int c0, int pb, int warp, int lane) {
-  static_assert(BR == 32 * BQ_ROW_WARPS, "one 32-row slab per row warp");
-  const bool roww = warp < BQ_ROW_WARPS;          // warps 8..15 only take part in the barriers
-  constexpr int LDS = BR + 4;
-  double* red = scratch;            // [2][8 values][8 warps]
-  double* drow = scratch + 128;     // [2][8]
-  double* Gs = scratch + 144;       // [8 warps][64]
-  double* Gtot = scratch + 656;     // [64]
-  const int i = roww ? 32 * warp + lane : 0;
-  double a[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) a[c] = (c < pb && roww) ? S[(size_t)(c0 + c) * LDS + i] : 0.0;
-  double tau[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    tau[r] = 0.0;
-    if (r < pb) {
-      const int d = c0 + r;
-      const int b = r & 1;
-      if (roww) {
-        double p[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) p[c] = (c >= r && i > d) ? a[r] * a[c] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) if (c >= r) p[c] += __shfl_xor_sync(0xffffffffu, p[c], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) if (c >= r) red[b * 64 + c * 8 + warp] = p[c];
-        }
-        if (i == d) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) drow[b * 8 + c] = a[c];
-        }
-      }
-      __syncthreads();
-      if (!roww) continue;
-      double tot[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        tot[c] = 0.0;
-        if (c >= r) {
-          const double2* q = reinterpret_cast<const double2*>(red + b * 64 + c * 8);
-          const double2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-          tot[c] = ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
-        }
-      }
-      const double tail = tot[r], x0 = drow[b * 8 + r];
-      double beta, scale;
-      if (tail <= DBL_MIN) { tau[r] = 0.0; beta = x0; scale = 0.0; }
-      else {
-        // beta = -sign(x0) ||x||, tau = (beta - x0)/beta = 1 + |x0|/||x||, scale = 1/(x0 - beta) = sign(x0)/(|x0| + ||x||):
-        // one rsqrt and one reciprocal instead of a square root and two divisions on the reflector's critical path
-        const double n2 = fma(x0, x0, tail);
-        const double inrm = rsqrt(n2);
-        const double nrm = n2 * inrm;
-        const double ax = fabs(x0);
-        beta = (x0 >= 0.0) ? -nrm : nrm;
-        tau[r] = fma(ax, inrm, 1.0);
-        const double rc = __drcp_rn(ax + nrm);
-        scale = (x0 >= 0.0) ? rc : -rc;
-      }
-      const double v = (i > d) ? a[r] * scale : (i == d ? 1.0 : 0.0);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (c > r && c < pb) {
-          const double w = tau[r] * fma(scale, tot[c], drow[b * 8 + c]);
-          a[c] = fma(-w, v, a[c]);
-        }
-      }
-      if (i > d) a[r] = v; else if (i == d) a[r] = beta;
-    }
-  }
-  // storage form back to S; clean reflectors to Vp
-  if (roww) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      if (c < pb) S[(size_t)(c0 + c) * LDS + i] = a[c];
-      const int d = c0 + c;
-      Vp[(size_t)c * LDS + i] = (c < pb) ? ((i > d) ? a[c] : (i == d ? 1.0 : 0.0)) : 0.0;
-    }
-  }
-  __syncthreads();
-  // Gram partial of this warp's 32 rows on the tensor cores: G = V^T V (A and B fragments are the same values)
-  if (roww) {
-    const int g = lane >> 2, t = lane & 3;
-    double acc[2] = {0.0, 0.0};
-    if (32 * warp + 31 >= c0) {
-      const double* vg = Vp + (size_t)g * LDS + 32 * warp + t;
-#pragma unroll
-      for (int k0 = 0; k0 < 32; k0 += 4) { const double x = vg[k0]; dmma884(acc, x, x); }
-    }
-    Gs[warp * 64 + g + 8 * (2 * t)] = acc[0];
-    Gs[warp * 64 + g + 8 * (2 * t + 1)] = acc[1];
-  }
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    double s2 = 0.0;
-#pragma unroll
-    for (int w = 0; w < BQ_ROW_WARPS; ++w) s2 += Gs[w * 64 + threadIdx.x];
-    Gtot[threadIdx.x] = s2;
-  }
-  __syncthreads();
-  // T by the dlarft recurrence, one row per thread: T[s][s] = tau_s, T[s][i] = -tau_i * sum_{r=s}^{i-1} T[s][r] G[r][i]
-  if (threadIdx.x < 8) {
-    const int srow = threadIdx.x;
-    double trow[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      double val = 0.0;
-      if (c == srow) val = tau[c];
-      else if (c > srow) {
-        double acc = 0.0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) if (r < c && r >= srow) acc = fma(trow[r], Gtot[r + 8 * c], acc);
-        val = -tau[c] * acc;
-      }
-      trow[c] = val;
-      Tsm[srow + 8 * c] = val;
-      Tglob[srow + 8 * c] = val;
-    }
-    double tv = 0.0;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) if (c == srow) tv = tau[c];
-    if (srow < pb) tau_s[c0 + srow] = tv;
-  }
-}
-
 // Transposing warp reduction of 8 per-lane values: after three halving exchanges (xor 16, 8, 4) every lane owns ONE column,
 // two more butterfly steps finish the sum.  9 shuffles instead of 40; returns the total of column `col` (valid in all lanes,
 // lanes with (lane & 3) == 0 publish it).
@@ -822,47 +674,6 @@ k_house_factor_la(double* __restrict__ Y, long long ldy, long long rows, int l, 
   for (int j = threadIdx.x; j < l; j += BQ_THREADS) tau_g[(size_t)blockIdx.x * l + j] = tau_s[j];
 }
 
-template <int BR>
-__global__ void __launch_bounds__(BQ_THREADS, 1)
-k_house_factor_blk(double* __restrict__ Y, long long ldy, long long rows, int l, double* __restrict__ tau_g,
-                   double* __restrict__ Rstack, long long ldr, double* __restrict__ Tg, int dbg) {
-  constexpr int LDS = BR + 4;
-  extern __shared__ double sm[];
-  double* S = sm;
-  double* Vp = S + (size_t)l * LDS;
-  double* Tsm = Vp + (size_t)8 * LDS;
-  double* scratch = Tsm + 64;                      // 720 doubles, see panel_factor
-  double* tau_s = scratch + 720;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long r0 = (long long)blockIdx.x * BR;
-  const int nrows = (int)min((long long)BR, rows - r0);
-  const int npanels = (l + 7) / 8;
-
-  for (int k = warp; k < l; k += BQ_WARPS) {
-    const double* src = Y + (size_t)k * ldy + r0;
-    for (int i = lane; i < BR; i += 32) S[(size_t)k * LDS + i] = (i < nrows) ? src[i] : 0.0;
-  }
-  __syncthreads();
-  double* Tblock = Tg + (size_t)blockIdx.x * npanels * 64;
-  for (int p = 0; p < npanels; ++p) {
-    const int c0 = 8 * p, pb = min(8, l - c0);
-    if (!(dbg & 2)) panel_factor<BR>(S, Vp, Tsm, tau_s, Tblock + (size_t)p * 64, scratch, c0, pb, warp, lane);
-    __syncthreads();
-    if (c0 + pb < l && !(dbg & 1)) block_reflect<BR>(S, Vp, Tsm, c0, c0 + pb, l, warp, BQ_WARPS, lane, true);
-    __syncthreads();
-  }
-  double* Rb = Rstack + (size_t)blockIdx.x * l;
-  for (int k = warp; k < l; k += BQ_WARPS) {
-    double* dst = Y + (size_t)k * ldy + r0;
-    for (int i = lane; i < BR; i += 32) {
-      const double val = S[(size_t)k * LDS + i];
-      if (i < nrows) dst[i] = val;
-      if (i < l) Rb[(size_t)k * ldr + i] = (i <= k) ? val : 0.0;
-    }
-  }
-  for (int j = threadIdx.x; j < l; j += BQ_THREADS) tau_g[(size_t)blockIdx.x * l + j] = tau_s[j];
-}
-
 // Up to 16 tree levels can be processed by one launch (their blocks are independent when every level starts from the
 // identity): the block looks its level up in this table.
 struct ApplyLevel { const double* V; long long ldv; long long rows; const double* Tg; const double* Ctop; long long ldc; double* Q; long long ldq; int first_block; };
@@ -1075,16 +886,13 @@ int pick_br(int l) {
 }
 
 int cl_max_nodes() { static int m = -1; if (m < 0) { const char* e = getenv("RSVDB_TSQR_CL_MAX"); m = e ? atoi(e) : 99; } return m; }
-int dbg_mode() { static int m = -1; if (m < 0) { const char* e = getenv("RSVDB_TSQR_DEBUG"); m = e ? atoi(e) : 0; } return m; }   // timing experiments only
 
 size_t blk_smem_bytes(int l) { return ((size_t)(l + 8) * (256 + 4) + 64 + 720 + (size_t)l) * sizeof(double); }
 
 cudaError_t set_attr_blk_once() {
   static bool done = false;
   if (done) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(k_house_factor_blk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_house_apply_blk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(k_house_apply_blk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_house_factor_la<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
@@ -1122,7 +930,7 @@ cudaError_t Tsqr::plan(long long rows, int l) {
     off_top_ = need; need += (size_t)l * l;
     off_scratch_ = need; need += (size_t)std::max<long long>(r, 1) * l;   // apply_global cannot run in place
   } else {
-    const bool use_cl = blk_ && !(dbg_mode() & 8) && cl_factor_smem(l) <= 227 * 1024 && cl_apply_smem(l) <= 227 * 1024;
+    const bool use_cl = blk_ && cl_factor_smem(l) <= 227 * 1024 && cl_apply_smem(l) <= 227 * 1024;
     for (;;) {
       Level L; L.rows = r;
       // leaves: 256-row single-CTA blocks (all SMs busy); upper levels and mid-sized panels: 1024-row cluster nodes
@@ -1165,8 +973,6 @@ cudaError_t Tsqr::factor(cudaStream_t st, double* Y, long long ldy, int* launche
       e = set_attr_blk_once(); if (e != cudaSuccess) return e;
       if (L.cl)
         k_node_factor_cl<<<L.nb * CL, BQ_THREADS, cl_factor_smem(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
-      else if (dbg_mode() & 4)
-        k_house_factor_blk<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T, dbg_mode());
       else
         k_house_factor_la<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
     } else
