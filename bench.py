@@ -43,7 +43,7 @@ SAMPLE_ROWS = 20000            # bounded CPU sample: the first 20000 rows of the
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=M_FULL)      # development overrides; the driver never passes them

@@ -31,3 +31,36 @@ def rsvd_sharded(A_p, Omega, l, q, dist, torch, O):
     Bt = _allreduce(A_p.T @ Q_p, dist, torch)                           # B^T = A^T Q
     Ut, S, V, _ = O.svd_jacobi(Bt.T)                                    # replicated small SVD
     return Q_p @ Ut, S, V
+
+
+def column_stats_sharded(A_p, normalize, dist, torch):
+    """pca.cu column_stats: all-reduce [column sums | row count], mean; then all-reduce the centred sums of squares."""
+    n = A_p.shape[1]
+    tot = _allreduce(np.r_[A_p.sum(axis=0), float(A_p.shape[0])], dist, torch)
+    mean = tot[:n] / tot[n]
+    inv_sd = None
+    if normalize:
+        css = _allreduce(((A_p - mean) ** 2).sum(axis=0), dist, torch)
+        inv_sd = 1.0 / np.sqrt(css / (tot[n] - 1.0))
+    return mean, inv_sd
+
+
+def rpca_sharded(A_p, Omega, l, q, normalize, dist, torch, O):
+    """pipeline.cu with a Centering: the products stream the UNCENTRED shard; (A - 1 mu^T) D X = A (D X) - 1 (mu^T D X) needs no
+    exchange, D (A^T - mu 1^T) Q = D (A^T Q - mu (1^T Q)) is corrected per shard BEFORE the all-reduce (it is linear)."""
+    mean, inv_sd = column_stats_sharded(A_p, normalize, dist, torch)
+    D = np.ones(A_p.shape[1]) if inv_sd is None else inv_sd
+
+    def an(X):
+        Xs = X * D[:, None]
+        return A_p @ Xs - (mean @ Xs)[None, :]
+
+    def at(Q_p):
+        return _allreduce((A_p.T @ Q_p - np.outer(mean, Q_p.sum(axis=0))) * D[:, None], dist, torch)
+
+    Q_p, _ = tsqr_sharded(an(Omega), dist, torch, O)
+    for _ in range(q):
+        Qz, _ = O.householder_qr(at(Q_p))
+        Q_p, _ = tsqr_sharded(an(Qz), dist, torch, O)
+    Ut, S, V, _ = O.svd_jacobi(at(Q_p).T)
+    return mean, inv_sd, Q_p @ Ut, S, V

@@ -96,3 +96,38 @@ def test_sharded_rsvd_two_gloo_ranks(tmp_path, oracle):
     assert np.linalg.norm(U.T @ U - np.eye(l)) < 1e-12
     assert abs(oracle.reconstruction_error(A, U, S, V) - oracle.reconstruction_error(A, Uo, So, Vo)) < 1e-9 * np.linalg.norm(A)
     assert oracle.subspace_sin_theta(Uo, U) < 1e-8
+
+
+def _rpca_worker(rank, world, port, m, n, l, q, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle import rsvd_oracle as O
+    import sharded_model
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    A = W.c3_pca(m, n, seed=9) * (1.0 + (np.arange(n) % 7)) + 4.0 * np.random.default_rng(5).standard_normal(n)
+    off, rows = W.row_split(m, world, rank)
+    mean, inv_sd, U_p, S, V = sharded_model.rpca_sharded(A[off:off + rows], W.omega(n, l), l, q, True, dist, torch, O)
+    np.savez(Path(out_dir) / f"p{rank}.npz", U=U_p, S=S, V=V, mean=mean, inv_sd=inv_sd)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_randomized_pca_two_gloo_ranks(tmp_path, oracle):
+    """The row-sharded implicit-centring path (pca.cu column_stats + pipeline.cu Centering) restated with numpy + gloo on
+    2 CPU ranks equals the oracle's rSVD of the explicitly centred and scaled matrix."""
+    import torch.multiprocessing as mp
+    m, n, l, q, world = 401, 90, 10, 2, 2
+    mp.spawn(_rpca_worker, args=(world, _free_port(), m, n, l, q, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"p{r}.npz") for r in range(world)]
+    U = np.vstack([p["U"] for p in parts]); S = parts[0]["S"]; V = parts[0]["V"]
+    assert np.array_equal(parts[0]["S"], parts[1]["S"]) and np.array_equal(parts[0]["mean"], parts[1]["mean"])
+    A = W.c3_pca(m, n, seed=9) * (1.0 + (np.arange(n) % 7)) + 4.0 * np.random.default_rng(5).standard_normal(n)
+    C = A - A.mean(axis=0); C = C / np.sqrt((C * C).sum(axis=0) / (m - 1))
+    np.testing.assert_allclose(parts[0]["mean"], A.mean(axis=0), rtol=1e-13)
+    Uo, So, Vo = oracle.rsvd(C, W.omega(n, l), l, q, oracle.JACOBI)
+    assert oracle.sigma_close(S, So)[0]
+    assert abs(oracle.reconstruction_error(C, U, S, V) - oracle.reconstruction_error(C, Uo, So, Vo)) < 1e-9 * np.linalg.norm(C)
+    assert np.linalg.norm(U.T @ U - np.eye(l)) < 1e-11

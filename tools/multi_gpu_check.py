@@ -42,6 +42,29 @@ for (m, n, l, q, gen) in [(3001, 400, 32, 2, "pod"), (20000, 1500, 100, 2, "gaus
         ok = okS and eg <= eo + 1e-8 * np.linalg.norm(A) and orthU < 1e-10 and same_S
         ok_all &= ok
         print(json.dumps({"multi_gpu": [m, n, l, q, gen], "world": world, "ok": bool(ok), "relS": relS, "err_gpu": eg, "err_oracle": eo, "orthU": orthU, "S_identical_on_all_ranks": same_S}), flush=True)
+# randomized PCA on row shards: column statistics are all-reduced, the centring corrections are applied per shard
+for (m, n, l, normalize) in [(20001, 300, 20, True), (6000, 500, 32, False)]:
+    rng = np.random.default_rng(5)
+    A = W.c3_pca(m, n, seed=9) * (1.0 + (np.arange(n) % 7)) + 4.0 * rng.standard_normal(n)
+    Om = W.omega(n, l)
+    off, rows = W.row_split(m, world, rank)
+    mean, sd, U_p, S, V = E.rpca(A[off:off + rows], l, normalize, SVDMethod.Jacobi, Om, 2)
+    Ut = torch.from_numpy(np.ascontiguousarray(U_p)).to(dev)
+    parts = [torch.empty((W.row_split(m, world, r)[1], U_p.shape[1]), dtype=torch.float64, device=dev) for r in range(world)]
+    dist.all_gather(parts, Ut)
+    U = torch.cat(parts, 0).cpu().numpy()
+    if rank == 0:
+        mu = A.sum(axis=0) / m; C = A - mu
+        ok = bool(np.allclose(mean, mu, rtol=1e-12, atol=1e-12))
+        if normalize:
+            s = np.sqrt((C * C).sum(axis=0) / (m - 1)); C = C / s
+            ok &= bool(np.allclose(sd, s, rtol=1e-12))
+        Uo, So, Vo = O.rsvd(np.asfortranarray(C), Om, l, 2, O.JACOBI)
+        okS, relS = O.sigma_close(S, So)
+        eg, eo = O.reconstruction_error(C, U, S, V), O.reconstruction_error(C, Uo, So, Vo)
+        ok &= okS and eg <= eo + 1e-8 * np.linalg.norm(C)
+        ok_all &= ok
+        print(json.dumps({"multi_gpu_rpca": [m, n, l, normalize], "world": world, "ok": bool(ok), "relS": relS, "err_gpu": eg, "err_oracle": eo}), flush=True)
 if rank == 0:
     print(json.dumps({"all_ok": bool(ok_all)}), flush=True)
 E.close()
