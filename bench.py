@@ -32,9 +32,9 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-# the contract is ONE JSON line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# the contract is ONE JSON line on stdout: NCCL prints its "NCCL version ..." banner (NCCL_DEBUG=VERSION / WARN) and its
+# INFO log to stdout unless told otherwise -- send them to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 M_FULL, N_FULL, L_FULL, Q_FULL = 200000, 20000, 100, 2
 SAMPLE_ROWS = 20000            # bounded CPU sample: the first 20000 rows of the same matrix (1/10 of the work)
