@@ -32,8 +32,10 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-# the contract is ONE JSON line on stdout: NCCL prints its "NCCL version ..." banner (NCCL_DEBUG=VERSION / WARN) and its
-# INFO log to stdout unless told otherwise -- send them to stderr
+# the contract is ONE JSON line on stdout.  NCCL writes its "NCCL version ..." banner and its log to stdout; NCCL_DEBUG_FILE
+# redirects them, but only for levels above VERSION -- so VERSION is raised to WARN (same banner, no extra output)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 M_FULL, N_FULL, L_FULL, Q_FULL = 200000, 20000, 100, 2
