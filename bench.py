@@ -157,6 +157,20 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_cpus(torch, local):
+    """Pin this rank to the CPUs next to its GPU (NVML's ideal affinity) so that the pinned host buffers of the end-to-end
+    leg are allocated on the GPU's NUMA node -- what an MPI launcher's binding does for the reference.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(local)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0".encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -164,6 +178,7 @@ def run_ours(args):
     from rsvd_kamaneh_raganato_terrana_b200 import Engine, SVDMethod, workloads as W
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    bound_cpus = bind_to_gpu_cpus(torch, local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
@@ -265,7 +280,8 @@ def run_ours(args):
         dt = float(tt.item())
         e2e = {"value": round(F / dt * 1e-9, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": int(8 * (rows * n + n * l)),
                "d2h_bytes_per_step": int(8 * (rows * l + l + n * l)), "ms_per_step": round(dt * 1e3, 2), "steps": args.e2e_steps,
-               "sigma_matches_device_path": bool(np.max(np.abs(Sh.numpy() - s_dev) / s_dev[0]) < 1e-12)}
+               "sigma_matches_device_path": bool(np.max(np.abs(Sh.numpy() - s_dev) / s_dev[0]) < 1e-12),
+               "host_cpus_bound_per_rank": bound_cpus}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
