@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kThreads) k_col_reduce(const double* __restric
       const double x = col[0];
       acc0 = (MODE == 1) ? (x - sh) * (x - sh) : (aux ? aux[0] * x : x);
     }
-    const long long pairs = (rows - i0) >> 1;
+    const long long pairs = rows > i0 ? (rows - i0) >> 1 : 0;
     const double2* c2 = reinterpret_cast<const double2*>(col + i0);
     for (long long p = threadIdx.x; p < pairs; p += kThreads) {
       const double2 v = c2[p];
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kThreads) k_center_scale(double* __restrict__ 
     const double mu = mean[j], dv = sd ? sd[j] : 1.0;
     long long i0 = ((reinterpret_cast<uintptr_t>(col) & 15) != 0) ? 1 : 0;
     if (i0 == 1 && threadIdx.x == 0 && blockIdx.y == 0 && rows > 0) col[0] = sd ? (col[0] - mu) / dv : col[0] - mu;
-    const long long pairs = (rows - i0) >> 1;
+    const long long pairs = rows > i0 ? (rows - i0) >> 1 : 0;
     double2* c2 = reinterpret_cast<double2*>(col + i0);
     for (long long p = (long long)blockIdx.y * kThreads + threadIdx.x; p < pairs; p += (long long)gridDim.y * kThreads) {
       double2 v = c2[p];

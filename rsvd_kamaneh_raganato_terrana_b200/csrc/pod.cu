@@ -40,9 +40,13 @@ __global__ void k_power_vref(const double* __restrict__ Vc, long long ldv, int b
   for (int i = blockIdx.y; i < r; i += gridDim.y) out[(size_t)i * ldo + j] = (j < k) ? Vc[(size_t)j * ldv + i] : (j == i ? 1.0 : 0.0);
 }
 
-struct Arena {
-  double* base; size_t off = 0, cap;
-  double* take(size_t d) { double* p = base + off; off += (d + 31) & ~size_t(31); return p; }
+struct Arena {   // bump allocator over pod_ws; an undersized plan is reported (overflow) instead of running past the buffer
+  double* base; size_t off = 0, cap; bool overflow = false;
+  double* take(size_t d) {
+    const size_t padded = (d + 31) & ~size_t(31);
+    if (off + padded > cap) { overflow = true; return base; }
+    double* p = base + off; off += padded; return p;
+  }
 };
 
 struct SvdOut {
@@ -71,14 +75,15 @@ int perform_svd(rsvdb_ctx* c, Arena& ar, const double* M, int64_t a, int64_t b, 
       if (r > k) return fail(c, -1, "POD: r larger than min(rows, cols) of the matrix handed to SVD<Power>");
       if (a > 16384) return fail(c, -6, "POD: SVD<Power> returns a rows x rows U; more than 16384 rows is not supported");
       double* Mt = ar.take((size_t)b * a);
-      RSVDB_TRY(transpose2d(c, M, ldm, Mt, b, a, b));
       o->U = ar.take((size_t)a * a); o->ldu = a; o->ucols = a;
       o->sigma = ar.take((size_t)k); o->slen = k;
       double* Vc = ar.take((size_t)b * r);
+      o->Vr = ar.take((size_t)b * r); o->ldvr = b;
+      if (ar.overflow) return fail(c, -4, "POD: workspace plan too small");
+      RSVDB_TRY(transpose2d(c, M, ldm, Mt, b, a, b));
       int found = 0;
       RSVDB_TRY(small_svd_power_t(c, Mt, b, a, b, r, seed, o->U, a, (int)a, o->sigma, Vc, b, &found));
       if (found < r) return fail(c, -5, "POD: SVD<Power> met a singular value below 1e-12 before r were found (the reference then indexes past the end)");
-      o->Vr = ar.take((size_t)b * r); o->ldvr = b;
       k_power_vref<<<dim3((unsigned)((b + 255) / 256), (unsigned)std::min(r, 64)), 256, 0, c->stream>>>(Vc, b, (int)b, r, r, o->Vr, b);
       RSVDB_CUDA(c, cudaGetLastError()); ++c->launches;
       return 0;
@@ -88,6 +93,7 @@ int perform_svd(rsvdb_ctx* c, Arena& ar, const double* M, int64_t a, int64_t b, 
       o->U = ar.take((size_t)a * k); o->ldu = a; o->ucols = k;
       o->sigma = ar.take((size_t)k); o->slen = k;
       double* V = ar.take((size_t)b * k);
+      if (ar.overflow) return fail(c, -4, "POD: workspace plan too small");
       RSVDB_TRY(small_svd_jacobi(c, M, ldm, nullptr, 0, a, b, o->U, a, o->sigma, V, b));
       o->Vr = V; o->ldvr = b;
       return 0;
@@ -97,16 +103,16 @@ int perform_svd(rsvdb_ctx* c, Arena& ar, const double* M, int64_t a, int64_t b, 
       if (r > b) return fail(c, -1, "POD: r larger than the column count of the matrix handed to rSVD");
       double* Om = nullptr; int64_t ldom = b;
       if (Omega) { Om = const_cast<double*>(Omega); ldom = ldo; }
-      else {
-        Om = ar.take((size_t)b * r);
-        RSVDB_TRY(rsvdb_generate_omega_dev(c, b, r, seed, Om, b));
-      }
+      else Om = ar.take((size_t)b * r);
       o->U = ar.take((size_t)a * r); o->ldu = a; o->ucols = r;
       o->sigma = ar.take((size_t)r); o->slen = r;
       double* V = ar.take((size_t)b * r);
+      double* Vr_pow = method == 1 ? ar.take((size_t)b * r) : nullptr;
+      if (ar.overflow) return fail(c, -4, "POD: workspace plan too small");
+      if (!Omega) RSVDB_TRY(rsvdb_generate_omega_dev(c, b, r, seed, Om, b));
       RSVDB_TRY(rsvd_device(c, M, a, b, ldm, Om, ldom, r, 2, method, o->U, a, o->sigma, V, b, seed));
       if (method == 1) {                                 // V is b x b with the vectors in rows
-        o->Vr = ar.take((size_t)b * r); o->ldvr = b;
+        o->Vr = Vr_pow; o->ldvr = b;
         k_power_vref<<<dim3((unsigned)((b + 255) / 256), (unsigned)std::min(r, 64)), 256, 0, c->stream>>>(V, b, (int)b, r, r, o->Vr, b);
         RSVDB_CUDA(c, cudaGetLastError()); ++c->launches;
       } else { o->Vr = V; o->ldvr = b; }
@@ -129,6 +135,7 @@ int gg(rsvdb_ctx* c, int ta, int tb, int64_t m, int64_t n, int64_t k, const doub
 int spd_sqrt(rsvdb_ctx* c, Arena& ar, const double* X, int64_t n, int64_t ldx, double* Xs, double* Xis) {
   if (n > 512) return fail(c, -6, "POD: matrix square root of an operator larger than 512 x 512 is not supported");
   double* U = ar.take((size_t)n * n); double* V = ar.take((size_t)n * n); double* s = ar.take((size_t)n); double* T = ar.take((size_t)n * n);
+  if (ar.overflow) return fail(c, -4, "POD: workspace plan too small");
   RSVDB_TRY(small_svd_jacobi(c, X, ldx, nullptr, 0, n, n, U, n, s, V, n));
   const dim3 g((unsigned)((n + 255) / 256), (unsigned)std::min<int64_t>(n, 64));
   k_scale_cols_fn<<<g, 256, 0, c->stream>>>(V, n, T, n, (int)n, (int)n, s, 0);
@@ -175,7 +182,14 @@ int pod_device(rsvdb_ctx* c, int variant, const double* S, int64_t Nh, int64_t n
   else {
     need = svd_scratch_doubles(d, d, r, svd_type) + (size_t)d * d + 64;
     if (ns > Nh) need += (size_t)ns * Nh + 64;                                        // S^T
-    if (variant >= POD_ENERGY) need += 8 * (size_t)d * d + 2 * (size_t)Nh * ns + (size_t)ns * ns * 6 + (size_t)Nh * Nh * 6 + 1024;
+    if (variant >= POD_ENERGY) {
+      if (ns <= Nh) {   // T = S^T Xh; weight: D^{1/2}, S D^{1/2} and the square root's scratch (U, V, T, s)
+        need += (size_t)ns * Nh + 256;
+        if (variant == POD_WEIGHT) need += 4 * (size_t)ns * ns + (size_t)Nh * ns + (size_t)ns + 1024;
+      } else {          // Xh^{1/2}, Xh^{-1/2}, the square root's scratch, T1, T2, T3
+        need += 6 * (size_t)Nh * Nh + 2 * (size_t)Nh * ns + (size_t)Nh + 1024;
+      }
+    }
   }
   need += 4096;
   RSVDB_CUDA(c, c->pod_ws.reserve(need * sizeof(double)));
@@ -194,6 +208,7 @@ int pod_device(rsvdb_ctx* c, int variant, const double* S, int64_t Nh, int64_t n
 
   const double* Smodes = S; int64_t ld_modes = lds;      // the matrix the modes are recovered from (S or S * D^{1/2})
   double* C = ar.take((size_t)d * d);
+  if (ar.overflow) return fail(c, -4, "POD: workspace plan too small");
   double* Xis = nullptr;                                 // Xh^{-1/2} for the ns > Nh energy / weight branches
   if (ns <= Nh) {
     if (variant == POD_STANDARD) {                       // C = S^T S                         POD.cpp:152
@@ -201,24 +216,28 @@ int pod_device(rsvdb_ctx* c, int variant, const double* S, int64_t Nh, int64_t n
     } else {
       if (variant == POD_WEIGHT) {                       // Stilde = S * D^{1/2}              POD.cpp:363-370
         double* Ds = ar.take((size_t)ns * ns); double* St = ar.take((size_t)Nh * ns);
+        if (ar.overflow) return fail(c, -4, "POD: workspace plan too small");
         RSVDB_TRY(spd_sqrt(c, ar, D, ns, ldd, Ds, nullptr));
         RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, S, Nh, ns, lds, Ds, ns, (int)ns, St, Nh, &nl));
         Smodes = St; ld_modes = Nh;
       }
       // Ctilde = (S^T Xh) S                                                          POD.cpp:250, :373
       double* T = ar.take((size_t)ns * Nh);
+      if (ar.overflow) return fail(c, -4, "POD: workspace plan too small");
       RSVDB_CUDA(c, gemm_at(c->gemm_ws, c->stream, c->nsm, Smodes, Nh, ns, ld_modes, Xh, ldx, (int)Nh, T, ns, 0, &nl));
       RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, T, ns, Nh, ns, Smodes, ld_modes, (int)ns, C, ns, &nl));
     }
   } else {
     if (variant == POD_STANDARD) {                       // K = S S^T                         POD.cpp:171
       double* St = ar.take((size_t)ns * Nh);
+      if (ar.overflow) return fail(c, -4, "POD: workspace plan too small");
       RSVDB_TRY(transpose2d(c, S, lds, St, ns, Nh, ns));
       RSVDB_CUDA(c, gemm_at(c->gemm_ws, c->stream, c->nsm, St, ns, Nh, ns, St, ns, (int)Nh, C, Nh, 0, &nl));
     } else {                                             // Ktilde = Xs S [D] S^T Xs          POD.cpp:272-280, :402-409
       double* Xs = ar.take((size_t)Nh * Nh); Xis = ar.take((size_t)Nh * Nh);
       RSVDB_TRY(spd_sqrt(c, ar, Xh, Nh, ldx, Xs, Xis));
       double* T1 = ar.take((size_t)Nh * ns); double* T2 = ar.take((size_t)Nh * ns); double* T3 = ar.take((size_t)Nh * Nh);
+      if (ar.overflow) return fail(c, -4, "POD: workspace plan too small");
       RSVDB_TRY(gg(c, 0, 0, Nh, ns, Nh, Xs, Nh, S, lds, T1, Nh));
       const double* L = T1;
       if (variant == POD_WEIGHT) { RSVDB_TRY(gg(c, 0, 0, Nh, ns, ns, T1, Nh, D, ldd, T2, Nh)); L = T2; }
