@@ -152,6 +152,9 @@ constexpr int JC = 4;
 
 __device__ __forceinline__ unsigned jc_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void jc_sync() {
+  // the .aligned forms need the whole warp converged; lanes of one warp take different branches in the pair loops
+  // (a dummy pair for odd k, idle 16-lane groups), so reconverge explicitly first
+  __syncwarp();
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void jc_store(double* p, unsigned rank, double v) {
@@ -276,12 +279,14 @@ k_jacobi_cl(const double* __restrict__ W, long long ldw, int k, int transpose_in
   // singular values: column norms summed over the cluster
   double* part = sig;                               // [k][JC]
   double* tot = sig + (size_t)k * JC;               // [k]
-  for (int j = grp; j < k; j += ngrp) {
+  // (the two 16-lane groups of a warp own different columns: keep the trip count uniform per warp, the shuffles are full-warp)
+  for (int j0 = 0; j0 < k; j0 += ngrp) {
+    const int j = j0 + grp; const bool on = j < k;
     double a = 0.0;
-    for (int i = hl; i < nr; i += 16) a = fma(X[(size_t)j * sr + i], X[(size_t)j * sr + i], a);
+    if (on) for (int i = hl; i < nr; i += 16) a = fma(X[(size_t)j * sr + i], X[(size_t)j * sr + i], a);
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (hl < JC) jc_store(part + (size_t)j * JC + rank, (unsigned)hl, a);
+    if (on && hl < JC) jc_store(part + (size_t)j * JC + rank, (unsigned)hl, a);
   }
   jc_sync();
   for (int j = tid; j < k; j += blockDim.x) {
@@ -291,12 +296,14 @@ k_jacobi_cl(const double* __restrict__ W, long long ldw, int k, int transpose_in
     tot[j] = sqrt(a);
   }
   __syncthreads();
-  for (int j = grp; j < k; j += ngrp) {
-    const double sj = tot[j];
+  for (int j0 = 0; j0 < k; j0 += ngrp) {
+    const int j = j0 + grp; const bool on = j < k;
+    const double sj = on ? tot[j] : 0.0;
     int r = 0;
-    for (int i = hl; i < k; i += 16) { const double si = tot[i]; r += (si > sj || (si == sj && i < j)) ? 1 : 0; }
+    if (on) for (int i = hl; i < k; i += 16) { const double si = tot[i]; r += (si > sj || (si == sj && i < j)) ? 1 : 0; }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (!on) continue;
     const double inv = (sj > 0.0) ? 1.0 / sj : 0.0;
     if (rank == 0 && hl == 0) So[r] = sj;
     for (int i = hl; i < nr; i += 16) {

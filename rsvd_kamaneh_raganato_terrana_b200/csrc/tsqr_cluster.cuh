@@ -15,6 +15,7 @@ constexpr int CL_ROWS = CL * 256;
 
 __device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();   // the .aligned forms need the whole warp converged
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ unsigned map_cluster(const void* p, unsigned rank) {

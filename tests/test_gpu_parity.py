@@ -864,3 +864,38 @@ def test_cpp_image_header(oracle, tmp_path):
     assert np.linalg.norm(fin[::2, ::2] - D) <= 2.0 * np.sqrt((sv[k:] ** 2).sum()) * (hi - lo) + 1e-6
     assert np.array_equal(fin[::2, ::2], fin[1::2, 1::2])                          # upscale(2) repeats pixels
     assert f"final {m} x {n}" in out and f"compressed file: U {m // 2} x {k + 10}" in out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# shape sweep: odd / wide / tiny sketches through every dispatch branch (cluster Jacobi with odd k once dead-locked here)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("m,n,l,q", [(50, 3000, 8, 2), (3000, 50, 50, 2), (777, 1234, 1, 2), (2048, 2048, 128, 1), (5000, 700, 150, 2),
+                                     (1500, 1500, 200, 0), (129, 257, 100, 3), (10000, 300, 104, 2), (640, 640, 101, 2), (4100, 90, 90, 2),
+                                     (33, 33, 33, 2), (2, 2, 1, 2), (9000, 2000, 96, 2), (600, 5000, 112, 1), (700, 700, 81, 1), (900, 400, 233, 1)])
+def test_rsvd_shape_sweep(engine, oracle, m, n, l, q):
+    rng = np.random.default_rng(2026 + m + 7 * n + 13 * l)
+    r = min(m, n, 60)
+    A = np.asfortranarray(rng.standard_normal((m, r)) @ np.diag(0.75 ** np.arange(r)) @ rng.standard_normal((r, n)) + 1e-7 * rng.standard_normal((m, n)))
+    Om = W.omega(n, l)
+    U, S, V = engine.rSVD(A, l, SVDMethod.Jacobi, Omega=Om, q=q)
+    Uo, So, Vo = oracle.rsvd(A, Om, l, q, oracle.JACOBI)
+    assert U.shape == Uo.shape and V.shape == Vo.shape and S.shape == So.shape
+    assert oracle.sigma_close(S, So)[0]
+    assert abs(oracle.reconstruction_error(A, U, S, V) - oracle.reconstruction_error(A, Uo, So, Vo)) <= 1e-8 * np.linalg.norm(A)
+    kk = min(U.shape[1], m)
+    assert np.linalg.norm(V.T @ V - np.eye(V.shape[1])) < 1e-9
+    if m >= U.shape[1]:
+        assert np.linalg.norm(U[:, :kk].T @ U[:, :kk] - np.eye(kk)) < 1e-9
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("k", [79, 80, 81, 83, 99, 101, 117, 151, 203, 233, 234, 257])
+def test_square_jacobi_svd_odd_and_boundary_sizes(engine, k):
+    rng = np.random.default_rng(k)
+    B = np.asfortranarray(rng.standard_normal((k, k)))
+    U, S, V = engine.svd(B, SVDMethod.Jacobi)
+    s = np.linalg.svd(B, compute_uv=False)
+    assert np.max(np.abs(S - s)) <= 1e-12 * s[0]
+    assert np.linalg.norm(U.T @ U - np.eye(k)) < 1e-11 and np.linalg.norm(V.T @ V - np.eye(k)) < 1e-11
+    assert np.linalg.norm(B - (U * S) @ V.T) <= 1e-11 * np.linalg.norm(B)
