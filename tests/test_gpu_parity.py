@@ -899,3 +899,26 @@ def test_square_jacobi_svd_odd_and_boundary_sizes(engine, k):
     assert np.max(np.abs(S - s)) <= 1e-12 * s[0]
     assert np.linalg.norm(U.T @ U - np.eye(k)) < 1e-11 and np.linalg.norm(V.T @ V - np.eye(k)) < 1e-11
     assert np.linalg.norm(B - (U * S) @ V.T) <= 1e-11 * np.linalg.norm(B)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("r,c", [(101, 640), (640, 101), (233, 90), (90, 233), (81, 81), (3, 500), (500, 3), (1, 7), (257, 300)])
+def test_svd_class_rectangular_sweep(engine, r, c):
+    rng = np.random.default_rng(r * 1000 + c)
+    B = np.asfortranarray(rng.standard_normal((r, c)))
+    U, S, V = engine.svd(B, SVDMethod.Jacobi)
+    k = min(r, c)
+    s = np.linalg.svd(B, compute_uv=False)
+    assert U.shape == (r, k) and V.shape == (c, k) and S.shape == (k,)
+    assert np.max(np.abs(S - s)) <= 1e-12 * s[0]
+    assert np.linalg.norm(B - (U * S) @ V.T) <= 1e-11 * np.linalg.norm(B)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("m,n", [(1001, 101), (300, 110), (257, 3), (5000, 97), (640, 233)])
+def test_qr_api_odd_shapes(engine, m, n):
+    rng = np.random.default_rng(m + n)
+    A = np.asfortranarray(rng.standard_normal((m, n)))
+    Q, R = engine.qr_decomposition_reduced(A)
+    assert np.linalg.norm(Q @ R - A) <= 1e-12 * np.linalg.norm(A)
+    assert np.linalg.norm(Q.T @ Q - np.eye(n)) < 1e-11 and np.all(np.diag(R) >= 0) and np.allclose(R, np.triu(R))
