@@ -11,6 +11,8 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    # pytest-timeout registers this itself when installed; declare it so the suite also collects cleanly without the plugin
+    config.addinivalue_line("markers", "timeout(seconds): per-test time limit (pytest-timeout)")
 
 
 @pytest.fixture(scope="session")
