@@ -922,3 +922,14 @@ def test_qr_api_odd_shapes(engine, m, n):
     Q, R = engine.qr_decomposition_reduced(A)
     assert np.linalg.norm(Q @ R - A) <= 1e-12 * np.linalg.norm(A)
     assert np.linalg.norm(Q.T @ Q - np.eye(n)) < 1e-11 and np.all(np.diag(R) >= 0) and np.allclose(R, np.triu(R))
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("m,n,l,q", [(3000, 1200, 33, 2), (500, 4000, 101, 1), (2500, 2500, 128, 2), (1500, 700, 7, 3), (900, 900, 1, 2)])
+def test_rsvd_csr_shape_sweep(engine, oracle, m, n, l, q):
+    A = _random_csr(m, n, 6, m + n + l)
+    Ad = np.asfortranarray(A.toarray()); Om = W.omega(n, l)
+    Ug, Sg, Vg = engine.rSVD_csr(A.indptr, A.indices, A.data, A.shape, l, SVDMethod.Jacobi, Omega=Om, q=q)
+    Uo, So, Vo = oracle.rsvd(Ad, Om, l, q, oracle.JACOBI)
+    assert oracle.sigma_close(Sg, So)[0]
+    assert abs(oracle.reconstruction_error(Ad, Ug, Sg, Vg) - oracle.reconstruction_error(Ad, Uo, So, Vo)) <= 1e-8 * np.linalg.norm(Ad)
