@@ -15,9 +15,13 @@ With N GPUs A is row-sharded (strong scaling: the matrix is fixed), one process 
                CUDA events inside the timed steps, against the measured FP64 DMMA peak (profiles/FP64_PEAKS.json;
                MEASURED_PEAKS.json carries no FP64 number)
   cpu_baseline the CPU oracle (numpy/OpenBLAS + LAPACK QR + C Jacobi: an Eigen-free restatement of the reference
-               algorithm -- the reference itself needs Eigen and MPI, absent from this image) on a bounded row sample
+               algorithm -- the reference itself needs Eigen and MPI, absent from this image): ONE full rSVD of the
+               SAME 200000 x 20000 matrix (about 20 s on the box's cores), whose singular values are also compared
+               with the device path's (sigma_parity_vs_oracle, tolerance 1e-8 relative, north_star)
 
---impl reference times that same CPU restatement as the reference arm.
+--impl reference times that same CPU restatement as the reference arm, on the full matrix (same config as our arm), with
+the BLAS thread count forced to the CPUs this process may run on (torchrun exports OMP_NUM_THREADS=1) and reported as
+the number of threads actually used.
 """
 from __future__ import annotations
 
@@ -32,6 +36,20 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+
+
+def _host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# The CPU legs use every host core this process may run on.  torch.distributed.run exports OMP_NUM_THREADS=1 to its
+# workers, which silently starved the reference arm at N >= 2 in round 1: override it BEFORE numpy/OpenBLAS load.
+if "reference" in sys.argv[1:] or any(a.startswith("--impl=reference") for a in sys.argv[1:]):
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_host_threads())
 # the contract is ONE JSON line on stdout.  NCCL writes its "NCCL version ..." banner and its log to stdout; NCCL_DEBUG_FILE
 # redirects them, but only for levels above VERSION -- so VERSION is raised to WARN (same banner, no extra output)
 if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -39,7 +57,7 @@ if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 M_FULL, N_FULL, L_FULL, Q_FULL = 200000, 20000, 100, 2
-SAMPLE_ROWS = 20000            # bounded CPU sample: the first 20000 rows of the same matrix (1/10 of the work)
+REF_WALL_BUDGET_S = 1200.0     # the reference arm stops early (and says so) rather than run past the driver's limit
 
 
 def parse():
@@ -115,23 +133,62 @@ def fp64_peak():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_oracle_gflops(A_sample, Om, l, q, steps=1, warmup=0):
-    """Time the CPU restatement on a host matrix; returns (GFLOP/s, seconds per step, threads)."""
+def blas_threads_in_use():
+    """Threads the BLAS behind numpy will actually use (threadpoolctl), not os.cpu_count()."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [int(d.get("num_threads", 0)) for d in threadpool_info() if d.get("user_api") == "blas"]
+        return max(n) if n else None
+    except Exception:
+        return None
+
+
+def cpu_oracle_gflops(A_host, Om, l, q, steps=1, warmup=0, wall_budget_s=None):
+    """Time the CPU restatement on a host matrix (F-order view, never copied); returns (GFLOP/s, s per step, threads, S,
+    steps actually timed, warm-up passes actually run).  With a wall budget the warm-up count, then the step count, are
+    cut (and reported) so that the run ends inside it."""
     from oracle import rsvd_oracle as O
+    from threadpoolctl import threadpool_limits
     O.build()
-    threads = os.cpu_count() or 1
-    for _ in range(warmup):
-        O.rsvd(A_sample, Om, l, q, O.JACOBI)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        U, S, V = O.rsvd(A_sample, Om, l, q, O.JACOBI)
-    dt = (time.perf_counter() - t0) / steps
-    m, n = A_sample.shape
-    return flops(m, n, l, q) / dt * 1e-9, dt, threads, S
+    want = _host_threads()
+    with threadpool_limits(limits=want, user_api="blas"):
+        threads = blas_threads_in_use() or want
+        t_start = time.perf_counter()
+        warmed = 0
+        for i in range(warmup):
+            tw = time.perf_counter()
+            O.rsvd(A_host, Om, l, q, O.JACOBI)
+            warmed += 1
+            per = time.perf_counter() - tw
+            if wall_budget_s is not None and (time.perf_counter() - t_start) + (warmup - warmed + steps) * per > wall_budget_s:
+                break                                             # keep the budget for the timed steps
+        done, S = 0, None
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            U, S, V = O.rsvd(A_host, Om, l, q, O.JACOBI)
+            done += 1
+            if wall_budget_s is not None and done < steps and (time.perf_counter() - t_start) + (time.perf_counter() - t0) / done > wall_budget_s:
+                break
+        dt = (time.perf_counter() - t0) / done
+    m, n = A_host.shape
+    return flops(m, n, l, q) / dt * 1e-9, dt, threads, S, done, warmed
+
+
+def host_matrix_c5(m, n, dev, chunk=20000):
+    """The full C5 matrix on the host as an F-order (column-major) m x n numpy view, generated block-wise on `dev`
+    (bit-identical to what the GPU arm holds) -- 32 GB at full size, allocated once, never copied."""
+    import numpy as np
+    import torch
+    from rsvd_kamaneh_raganato_terrana_b200 import workloads as W
+    At = torch.empty((n, m), dtype=torch.float64)                   # (n, m) C-order == column-major m x n
+    for r0 in range(0, m, chunk):
+        r = min(chunk, m - r0)
+        At[:, r0:r0 + r] = W.c5_shard_torch(m, n, r0, r, dev).cpu()
+    return At.numpy().T
 
 
 def run_reference(args):
-    """Reference arm: the reference's algorithm on the host cores (rank 0 only)."""
+    """Reference arm: the reference's algorithm (CPU restatement) on the host cores, full matrix, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -139,19 +196,22 @@ def run_reference(args):
     import torch
     from rsvd_kamaneh_raganato_terrana_b200 import workloads as W
     m, n, l, q = args.rows, args.cols, args.l, args.q
-    ms = min(SAMPLE_ROWS, m)
     dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
-    A = W.c5_shard_torch(m, n, 0, ms, dev).T.cpu().numpy()          # ms x n, column-major in memory
+    torch.set_num_threads(_host_threads())
+    A = host_matrix_c5(m, n, dev)
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
     Om = W.omega(n, l)
-    g, dt, threads, _ = cpu_oracle_gflops(A, Om, l, q, steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
+    g, dt, threads, _, done, warm = cpu_oracle_gflops(A, Om, l, q, steps=max(1, args.steps), warmup=max(0, args.warmup), wall_budget_s=REF_WALL_BUDGET_S)
     line = {
-        "impl": "reference", "metric": "rsvd_gflops", "value": round(g, 2), "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "impl": "reference", "metric": "rsvd_gflops", "value": round(g, 2), "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": done,
+        "warmup": warm, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"c5: rSVD rank-{l} q={q} of synthetic {m}x{n} FP64 (Jacobi back-end, host Omega)", "m": m, "n": n, "l": l, "q": q,
-                   "sample": f"first {ms} of {m} rows per step"},
+                   "steps_requested": args.steps, "warmup_requested": args.warmup},
         "cpu_baseline": {"value": round(g, 2), "unit": "GFLOP/s", "cores": threads, "kind": "port",
-                         "sample": f"first {ms} of {m} rows, full rSVD (numpy/OpenBLAS GEMM, LAPACK Householder QR, C Jacobi); the reference itself cannot be built (Eigen, MPI absent)"},
+                         "host_cpus_available": _host_threads(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
+                         "sample": f"the full {m}x{n} matrix, {done} complete rSVD(s) (numpy/OpenBLAS GEMM, LAPACK Householder QR, C Jacobi); the reference itself cannot be built (Eigen, MPI absent)"},
         "e2e": {"value": round(g, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -250,6 +310,8 @@ def run_ours(args):
                 "traffic": traffic, "traffic_note": "DRAM bytes per GEMM launch (ncu, profiles/r01_ncu_gemm_full_summary.txt); algorithmic bytes per launch = 8*rows*n",
                 "algorithmic_bytes_per_launch": 8.0 * rows * n, "kernel": "k_gemm_an<13> / k_gemm_at<13> (FP64 DMMA + TMA), 6 passes per step",
                 "peak_source": peak_src, "gemm_ms_per_step": round(gemm_ms, 3),
+                "whole_step_frac_of_peak": round(value * 1e-3 / (world * peak), 4),
+                "whole_step_note": "value / (n_gpus * peak): every phase (TSQR, small SVD, NCCL) counted; 'frac' covers the GEMM passes only",
                 "phase_ms_per_step": {k: round(v / args.steps, 3) for k, v in phases.items()},
                 "algorithmic_flops_per_launch": 2.0 * rows * n * l,
                 "hbm_GBps_of_A_stream": round((2 * q + 2) * 8.0 * rows * n / (gemm_ms * 1e-3) * 1e-9, 1) if gemm_ms > 0 else None}
@@ -284,15 +346,20 @@ def run_ours(args):
                "host_cpus_bound_per_rank": bound_cpus}
 
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        ms_rows = min(SAMPLE_ROWS, m)
+        # ONE full rSVD of the same matrix on the host cores (about 20 s): the CPU baseline and the parity check in one
         if e2e is not None:
-            A_s = Ah[:, :ms_rows].T.numpy()
+            A_h = Ah.numpy().T                                         # F-order m x n view of the pinned buffer
         else:
-            A_s = A[:, :ms_rows].T.cpu().numpy()
-        g, dts, threads, S_cpu = cpu_oracle_gflops(np.asfortranarray(A_s), W.omega(n, l), l, q, steps=1, warmup=0)
+            A_h = A.cpu().numpy().T
+        g, dts, threads, S_cpu, _, _ = cpu_oracle_gflops(A_h, W.omega(n, l), l, q, steps=1, warmup=0)
         cpu = {"value": round(g, 2), "unit": "GFLOP/s", "cores": threads, "kind": "port", "seconds": round(dts, 2),
-               "sample": f"first {ms_rows} of {m} rows, one full rSVD (numpy/OpenBLAS GEMM, LAPACK Householder QR, C Jacobi); reference itself unbuildable here (Eigen, MPI absent)"}
+               "sample": f"the full {m}x{n} matrix, one complete rSVD (numpy/OpenBLAS GEMM, LAPACK Householder QR, C Jacobi); reference itself unbuildable here (Eigen, MPI absent)"}
+        tol = 1e-8 * np.maximum(S_cpu, 1e-6 * S_cpu[0])
+        rel = np.abs(s_dev - S_cpu) / np.maximum(S_cpu, 1e-6 * S_cpu[0])
+        parity = {"max_rel_err": float(rel.max()), "tolerance": 1e-8, "ok": bool(np.all(np.abs(s_dev - S_cpu) <= tol)),
+                  "n_sigma": int(len(S_cpu)), "same_matrix": True}
 
     if rank == 0:
         line = {
@@ -303,7 +370,7 @@ def run_ours(args):
                        "m": m, "n": n, "l": l, "q": q, "rows_per_gpu": rows, "parallelism": f"row-shard x{world}",
                        "l2": "inputs larger than L2 (A shard is %.1f GB)" % (rows * n * 8 / 1e9), "time_to_rank_k_ms": round(ms_per_step, 3)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "sigma_head": [float(x) for x in s_dev[:4]],
+            "sigma_head": [float(x) for x in s_dev[:4]], "sigma_parity_vs_oracle": parity,
         }
         print(json.dumps(line), flush=True)
     eng.close()

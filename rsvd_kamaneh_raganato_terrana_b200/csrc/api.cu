@@ -48,7 +48,6 @@ __global__ void k_reciprocal(const double* __restrict__ x, double* __restrict__ 
   if (i < n) y[i] = 1.0 / x[i];
 }
 
-inline int64_t even_ld(int64_t rows) { return std::max<int64_t>(2, (rows + 1) & ~int64_t(1)); }
 
 int h2d(rsvdb_ctx* c, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
   if (rows <= 0 || cols <= 0) return 0;
@@ -68,6 +67,16 @@ int d2h(rsvdb_ctx* c, double* dst, int64_t ldd, const double* src, int64_t lds, 
   } else {
     RSVDB_CUDA(c, cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyDeviceToHost, c->stream));
   }
+  return 0;
+}
+
+// Host entry points synchronise anyway: report a Jacobi SVD that hit the sweep cap (negative sweep count) instead of
+// returning RSVDB_OK with unconverged factors.  (_dev callers query rsvdb_last_svd_info themselves.)
+int check_svd_converged(rsvdb_ctx* c) {
+  if (!c->d_svd_info) return 0;
+  int h[2] = {0, 0};
+  RSVDB_CUDA(c, cudaMemcpy(h, c->d_svd_info, sizeof(h), cudaMemcpyDeviceToHost));
+  if (h[0] < 0) return fail(c, RSVDB_ERR_NO_CONVERGENCE, "Jacobi SVD: sweep cap reached without convergence");
   return 0;
 }
 
@@ -137,6 +146,7 @@ int rsvdb_synchronize(rsvdb_ctx* c) {
 }
 const char* rsvdb_last_error(const rsvdb_ctx* c) { return c ? c->err.c_str() : "null context"; }
 int64_t rsvdb_launch_count(const rsvdb_ctx* c) { return c ? c->launches : 0; }
+int64_t rsvdb_generic_gemm_fallbacks(void) { return generic_fallback_count(); }
 
 int rsvdb_set_profiling(rsvdb_ctx* c, int enabled) {
   if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
@@ -188,6 +198,7 @@ int rsvdb_pm_iterations(int64_t ncols) { return pm_iterations(ncols); }
 int rsvdb_gemm_an_dev(rsvdb_ctx* c, const double* dA, int64_t m, int64_t n, int64_t lda, const double* dX, int64_t ldx,
                       int l, double* dY, int64_t ldy) {
   if (!c || m < 0 || n < 0 || l < 0 || lda < m || ldx < n || ldy < m) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "gemm_an: bad shape");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
   int k = 0;
   RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, dA, m, n, lda, dX, ldx, l, dY, ldy, &k));
   c->launches += k;
@@ -198,6 +209,7 @@ int rsvdb_gemm_at_dev(rsvdb_ctx* c, const double* dA, int64_t m, int64_t n, int6
                       int l, double* dZ, int64_t ldz, int transpose_out) {
   if (!c || m < 0 || n < 0 || l < 0 || lda < m || ldq < m || ldz < (transpose_out ? l : n))
     return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "gemm_at: bad shape");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
   int k = 0;
   RSVDB_CUDA(c, gemm_at(c->gemm_ws, c->stream, c->nsm, dA, m, n, lda, dQ, ldq, l, dZ, ldz, transpose_out, &k));
   c->launches += k;
@@ -206,6 +218,7 @@ int rsvdb_gemm_at_dev(rsvdb_ctx* c, const double* dA, int64_t m, int64_t n, int6
 
 int rsvdb_qr_dev(rsvdb_ctx* c, double* dY, int64_t rows, int l, int64_t ldy, int sharded, double* dR) {
   if (!c || rows < 0 || l <= 0 || ldy < rows) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "qr: bad shape");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
   const double* R = nullptr;
   RSVDB_TRY(qr_inplace(c, dY, rows, l, ldy, sharded != 0, &R));
   if (dR) RSVDB_CUDA(c, cudaMemcpyAsync(dR, R, (size_t)l * l * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -215,17 +228,20 @@ int rsvdb_qr_dev(rsvdb_ctx* c, double* dY, int64_t rows, int l, int64_t ldy, int
 int rsvdb_range_finder_dev(rsvdb_ctx* c, const double* dA, int64_t m, int64_t n, int64_t lda, const double* dOmega, int64_t ldo,
                            int l, int q, double* dQ, int64_t ldq) {
   if (!c || m < 0 || n <= 0 || lda < m || ldo < n || ldq < m) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "range_finder: bad shape");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
   return range_finder(c, dA, m, n, lda, dOmega, ldo, l, q, dQ, ldq);
 }
 
 int rsvdb_rsvd_dev(rsvdb_ctx* c, const double* dA, int64_t m, int64_t n, int64_t lda, const double* dOmega, int64_t ldo, int l,
                    int q, int method, uint64_t seed, double* dU, int64_t ldu, double* dS, double* dV, int64_t ldv) {
   if (!c || m < 0 || n <= 0 || lda < m || ldo < n || ldu < m || ldv < n) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "rsvd: bad shape");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
   return rsvd_device(c, dA, m, n, lda, dOmega, ldo, l, q, method, dU, ldu, dS, dV, ldv, seed);
 }
 
 int rsvdb_generate_omega_dev(rsvdb_ctx* c, int64_t n, int l, uint64_t seed, double* dOmega, int64_t ldo) {
   if (!c || n < 0 || l < 0 || ldo < n) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "generate_omega: bad shape");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
   if (n == 0 || l == 0) return RSVDB_OK;
   dim3 g((unsigned)((n + 255) / 256), (unsigned)std::min(l, 128));
   k_fill_normal<<<g, 256, 0, c->stream>>>(dOmega, ldo, n, l, seed);
@@ -289,6 +305,7 @@ int rsvdb_rsvd_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t
   RSVDB_TRY(d2h(c, S, k, dS, k, k, 1));
   RSVDB_TRY(d2h(c, V, ldv, dV, ldO, n, k));
   RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  RSVDB_TRY(check_svd_converged(c));
   return RSVDB_OK;
 }
 
@@ -350,6 +367,7 @@ int svd_host_impl(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t l
   RSVDB_TRY(d2h(c, S, k, dS, k, k, 1));
   RSVDB_TRY(d2h(c, V, ldv, dV, ldN, n, k));
   RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  RSVDB_TRY(check_svd_converged(c));
   if (found) *found = (int)k;
   return RSVDB_OK;
 }
@@ -435,6 +453,7 @@ int rsvdb_rpca_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t
   RSVDB_TRY(d2h(c, S, k, dS, k, k, 1));
   RSVDB_TRY(d2h(c, V, ldv, dV, ldO, n, k));
   RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  RSVDB_TRY(check_svd_converged(c));
   return RSVDB_OK;
 }
 
@@ -467,6 +486,7 @@ int rsvdb_pca_reconstruct_host(rsvdb_ctx* c, const double* pc, int64_t r, int k,
                                int64_t ldv, int64_t n, double* out, int64_t ldout) {
   if (!c || !pc || !mean || !V || !out || r <= 0 || n <= 0 || k <= 0 || ldp < r || ldv < n || ldout < r)
     return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "reconstructFromPCA: bad argument");
+  if (n > INT32_MAX) return fail(c, RSVDB_ERR_UNSUPPORTED, "reconstructFromPCA: more than 2^31-1 features");
   RSVDB_CUDA(c, cudaSetDevice(c->device));
   const int64_t ldR = even_ld(r), ldN = even_ld(n), ldK = even_ld(k);
   const size_t need = (IoArena::pad((size_t)ldR * k) + IoArena::pad((size_t)ldN * k) + IoArena::pad((size_t)ldK * n) + IoArena::pad((size_t)ldR * n) +
@@ -480,7 +500,7 @@ int rsvdb_pca_reconstruct_host(rsvdb_ctx* c, const double* pc, int64_t r, int k,
   RSVDB_TRY(h2d(c, dMean, n, mean, n, n, 1));
   RSVDB_TRY(transpose2d(c, dV, ldN, dVt, ldK, n, k));           // V^T (k x n) as the right operand
   int nl = 0;
-  if (n <= INT32_MAX) RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, dP, r, k, ldR, dVt, ldK, (int)n, dOut, ldR, &nl));
+  RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, dP, r, k, ldR, dVt, ldK, (int)n, dOut, ldR, &nl));
   c->launches += nl;
   RSVDB_TRY(add_row_vector(c, dOut, ldR, r, n, dMean, 1.0));
   RSVDB_TRY(d2h(c, out, ldout, dOut, ldR, r, n));
@@ -535,6 +555,7 @@ int rsvdb_pod_host(rsvdb_ctx* c, int variant, const double* S, int64_t Nh, int64
   RSVDB_TRY(d2h(c, W, ldw, dW, ldS, Nh, *N));             // the basis after conservativeResize(NoChange, N), POD.cpp:221
   RSVDB_TRY(d2h(c, sigma, sh.sigma_len, dSig, sh.sigma_len, sh.sigma_len, 1));
   RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  RSVDB_TRY(check_svd_converged(c));
   return RSVDB_OK;
 }
 
@@ -682,6 +703,7 @@ int rsvdb_pm_host(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t l
 
 int rsvdb_csr_spmm_dev(rsvdb_ctx* c, int64_t m, const int64_t* rp, const int32_t* ci, const double* v, const double* X, int l, double* Y) {
   if (!c || m < 0 || l <= 0) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "csr_spmm: bad shape");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
   return csr_spmm_rm(c, m, rp, ci, v, X, l, Y);
 }
 
@@ -689,6 +711,7 @@ int rsvdb_rsvd_csr_dev(rsvdb_ctx* c, int64_t m, int64_t n, int64_t nnz, const in
                        const double* dOmega, int64_t ldo, uint64_t seed, int l, int q, int method, double* dU, int64_t ldu, double* dS,
                        double* dV, int64_t ldv) {
   if (!c || m < 0 || n <= 0 || nnz < 0 || ldo < n || ldu < m || ldv < n) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "rsvd_csr: bad shape");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
   return rsvd_csr_device(c, m, n, nnz, rp, ci, v, dOmega, ldo, l, q, method, dU, ldu, dS, dV, ldv, seed);
 }
 
@@ -725,6 +748,7 @@ int rsvdb_rsvd_csr_host(rsvdb_ctx* c, int64_t m, int64_t n, int64_t nnz, const i
   RSVDB_TRY(d2h(c, S, k, dS, k, k, 1));
   RSVDB_TRY(d2h(c, V, ldv, dV, ldO, n, k));
   RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+  RSVDB_TRY(check_svd_converged(c));
   return RSVDB_OK;
 }
 

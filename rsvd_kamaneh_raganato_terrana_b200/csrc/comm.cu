@@ -15,7 +15,7 @@ typedef int (*fn_destroy)(void* comm);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int dtype, int op, void* comm, cudaStream_t);
 typedef int (*fn_allgather)(const void*, void*, size_t, int dtype, void* comm, cudaStream_t);
 typedef const char* (*fn_errstr)(int);
-constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
 
 struct Nccl {
   void* h = nullptr;
@@ -75,6 +75,13 @@ int comm_allreduce_sum(rsvdb_ctx* c, double* buf, size_t count) {
   if (c->nranks <= 1) return 0;
   int rc = nccl().allreduce(buf, buf, count, NCCL_FLOAT64, NCCL_SUM, c->nccl_comm, c->stream);
   if (rc != 0) return nccl_fail(c, rc, "ncclAllReduce");
+  return 0;
+}
+
+int comm_allreduce_max(rsvdb_ctx* c, double* buf, size_t count) {
+  if (c->nranks <= 1) return 0;
+  int rc = nccl().allreduce(buf, buf, count, NCCL_FLOAT64, NCCL_MAX, c->nccl_comm, c->stream);
+  if (rc != 0) return nccl_fail(c, rc, "ncclAllReduce(max)");
   return 0;
 }
 

@@ -12,6 +12,8 @@ int comm_init(rsvdb_ctx* c, int nranks, int rank, const void* id128);
 void comm_destroy(rsvdb_ctx* c);
 // in-place sum over ranks of `count` doubles
 int comm_allreduce_sum(rsvdb_ctx* c, double* buf, size_t count);
+// in-place max over ranks of `count` doubles
+int comm_allreduce_max(rsvdb_ctx* c, double* buf, size_t count);
 // gather `count` doubles from every rank into recv (nranks * count), rank-major
 int comm_allgather(rsvdb_ctx* c, const double* send, double* recv, size_t count);
 }  // namespace rsvdb

@@ -19,6 +19,7 @@
 //   K1: m-slot g <-> row 2g, m-slot g+8 <-> row 2g+1;  K2: m-slot g <-> column perm(g), m-slot g+8 <-> column 8+perm(g).
 // Work is cut into (tile, k-split) units; with nsplit > 1 each unit stores a partial tile to a workspace and a second
 // kernel sums the partials in a fixed order (bitwise reproducible; no atomics).
+#include "dev_once.cuh"
 #include "gemm_dmma.cuh"
 #include "ptx.cuh"
 
@@ -365,6 +366,8 @@ bool make_map(CUtensorMap* map, const double* base, long long rows, long long co
   return r == CUDA_SUCCESS;
 }
 
+static long long g_generic_fallbacks = 0;   // products that took the CUDA-core kernel because an operand was not TMA-addressable
+void note_generic_fallback() { ++g_generic_fallbacks; }
 bool tma_addressable(const double* p, long long ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 1) == 0; }
 
 // Cut the reduction into nsplit slabs so that (tiles x splits) fills the SMs in whole waves.  Cost model in units of one
@@ -392,11 +395,11 @@ template <int NB> cudaError_t launch_an(const CUtensorMap& tA, const CUtensorMap
   int stages = std::min(8, (int)((220 * 1024 - 1024) / STAGE));
   p.stages = stages;
   const size_t smem = (size_t)stages * STAGE + 1024 + 2 * stages * sizeof(uint64_t);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DevOnce attr_set;
+  if (!attr_set.get()) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_an<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.set();
   }
   k_gemm_an<NB><<<grid, NTHREADS, smem, st>>>(tA, tX, p);
   return cudaGetLastError();
@@ -406,17 +409,19 @@ template <int NB> cudaError_t launch_at(const CUtensorMap& tA, const CUtensorMap
   int stages = std::min(8, (int)((220 * 1024 - 1024) / STAGE));
   p.stages = stages;
   const size_t smem = (size_t)stages * STAGE + 1024 + 2 * stages * sizeof(uint64_t);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DevOnce attr_set;
+  if (!attr_set.get()) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_at<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.set();
   }
   k_gemm_at<NB><<<grid, NTHREADS, smem, st>>>(tA, tQ, p);
   return cudaGetLastError();
 }
 
 }  // namespace
+
+long long generic_fallback_count() { return g_generic_fallbacks; }
 
 cudaError_t gemm_generic(cudaStream_t st, int ta, int tb, int m, int n, int k, double alpha, const double* A, long long lda,
                          const double* B, long long ldb, double beta, double* C, long long ldc) {
@@ -433,7 +438,9 @@ cudaError_t gemm_an(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
     for (int n = 0; n < N; ++n) { cudaError_t e = cudaMemsetAsync(Y + (size_t)n * ldy, 0, (size_t)M * 8, st); if (e != cudaSuccess) return e; }
     return cudaSuccess;
   }
-  if (!tma_addressable(A, lda) || !tma_addressable(X, ldx) || M >= (1LL << 31) || K >= (1LL << 31)) {
+  if (M >= (1LL << 31) || K >= (1LL << 31)) return cudaErrorInvalidValue;     // explicit error: dimensions are 32-bit inside the kernels
+  if (!tma_addressable(A, lda) || !tma_addressable(X, ldx)) {
+    note_generic_fallback();
     if (launches) ++*launches;
     return gemm_generic(st, 0, 0, (int)M, N, (int)K, 1.0, A, lda, X, ldx, 0.0, Y, ldy);
   }
@@ -489,7 +496,9 @@ cudaError_t gemm_at(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
     else { for (long long j = 0; j < M; ++j) { cudaError_t e = cudaMemsetAsync(Z + (size_t)j * ldz, 0, (size_t)N * 8, st); if (e != cudaSuccess) return e; } }
     return cudaSuccess;
   }
-  if (!tma_addressable(A, lda) || !tma_addressable(Q, ldq) || M >= (1LL << 31) || K >= (1LL << 31)) {
+  if (M >= (1LL << 31) || K >= (1LL << 31)) return cudaErrorInvalidValue;
+  if (!tma_addressable(A, lda) || !tma_addressable(Q, ldq)) {
+    note_generic_fallback();
     if (launches) ++*launches;
     if (!transpose_out) return gemm_generic(st, 1, 0, (int)M, N, (int)K, 1.0, A, lda, Q, ldq, 0.0, Z, ldz);
     return gemm_generic(st, 1, 0, N, (int)M, (int)K, 1.0, Q, ldq, A, lda, 0.0, Z, ldz);

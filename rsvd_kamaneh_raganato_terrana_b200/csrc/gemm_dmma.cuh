@@ -29,4 +29,8 @@ cudaError_t gemm_at(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
 cudaError_t gemm_generic(cudaStream_t st, int ta, int tb, int m, int n, int k, double alpha, const double* A, long long lda,
                          const double* B, long long ldb, double beta, double* C, long long ldc);
 
+// Number of gemm_an / gemm_at calls (process-wide) that fell back to the CUDA-core kernel because an operand was not
+// TMA-addressable (odd leading dimension or a base pointer that is only 8-byte aligned).  A performance note, not an error.
+long long generic_fallback_count();
+
 }  // namespace rsvdb

@@ -9,6 +9,7 @@
 // Same singular values (to ~1e-15 relative, tighter than ParallelJacobi's own 1e-12 squared-weight stop), singular
 // vectors equal up to sign / rotation inside clusters.  Output order and sign follow the reference: S descending,
 // S >= 0 (:158-178).
+#include "dev_once.cuh"
 #include "jacobi.cuh"
 
 #include <cfloat>
@@ -330,9 +331,9 @@ cudaError_t jacobi_svd_square(GemmWorkspace& ws, cudaStream_t st, const double* 
     if (!cl_off && k >= 80 && cl_smem <= 220 * 1024 && sr <= 64) {
       const int rplc = (sr + 15) / 16;
 #define JCL(R)                                                                                                         \
-      { static bool attr = false;                                                                                      \
-        if (!attr) { cudaError_t e = cudaFuncSetAttribute(k_jacobi_cl<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
-                     if (e != cudaSuccess) return e; attr = true; }                                                    \
+      { static DevOnce attr;                                                                                           \
+        if (!attr.get()) { cudaError_t e = cudaFuncSetAttribute(k_jacobi_cl<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
+                     if (e != cudaSuccess) return e; attr.set(); }                                                    \
         k_jacobi_cl<R><<<JC, 1024, cl_smem, st>>>(W, ldw, k, transpose_in, U, ldu, S, Z, ldz, 60, d_info); }
       if (rplc <= 1) JCL(1) else if (rplc <= 2) JCL(2) else if (rplc <= 3) JCL(3) else JCL(4)
 #undef JCL
@@ -351,9 +352,9 @@ cudaError_t jacobi_svd_square(GemmWorkspace& ws, cudaStream_t st, const double* 
   const int threads = k >= 48 ? 1024 : (k >= 24 ? 512 : 256);
   const int rpl = (k + 15) / 16;
 #define JLAUNCH(R)                                                                                                   \
-  { static bool attr = false;                                                                                        \
-    if (!attr) { cudaError_t e = cudaFuncSetAttribute(k_jacobi<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
-                 if (e != cudaSuccess) return e; attr = true; }                                                      \
+  { static DevOnce attr;                                                                                             \
+    if (!attr.get()) { cudaError_t e = cudaFuncSetAttribute(k_jacobi<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
+                 if (e != cudaSuccess) return e; attr.set(); }                                                      \
     k_jacobi<R><<<1, threads, smem, st>>>(W, ldw, k, transpose_in, U, ldu, S, Z, ldz, Xg, Zg, use_smem, 60, d_info); }
   if (rpl <= 1) JLAUNCH(1) else if (rpl <= 2) JLAUNCH(2) else if (rpl <= 4) JLAUNCH(4) else if (rpl <= 7) JLAUNCH(7) else if (rpl <= 8) JLAUNCH(8)
   else if (rpl <= 16) JLAUNCH(16) else JLAUNCH(32)

@@ -23,17 +23,18 @@ __global__ void k_restack(const double* __restrict__ gathered, double* __restric
   }
 }
 
-__global__ void k_transpose(const double* __restrict__ src, long long lds, double* __restrict__ dst, long long ldd, int rows, int cols) {
-  // dst (cols x rows) = src (rows x cols)^T
+__global__ void k_transpose(const double* __restrict__ src, long long lds, double* __restrict__ dst, long long ldd, long long rows, long long cols,
+                            long long cblock0) {
+  // dst (cols x rows) = src (rows x cols)^T; grid.y covers column blocks [cblock0, cblock0 + gridDim.y)
   __shared__ double tile[32][33];
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const long long r0 = (long long)blockIdx.x * 32, c0 = (cblock0 + blockIdx.y) * 32;
   for (int cc = threadIdx.y; cc < 32; cc += 8) {
-    const int r = r0 + threadIdx.x, c = c0 + cc;
+    const long long r = r0 + threadIdx.x, c = c0 + cc;
     tile[cc][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)c * lds + r] : 0.0;
   }
   __syncthreads();
   for (int rr = threadIdx.y; rr < 32; rr += 8) {
-    const int r = r0 + rr, c = c0 + threadIdx.x;
+    const long long r = r0 + rr, c = c0 + threadIdx.x;
     if (r < rows && c < cols) dst[(size_t)r * ldd + c] = tile[threadIdx.x][rr];
   }
 }
@@ -47,10 +48,13 @@ __global__ void k_copy2d(const double* __restrict__ src, long long lds, double* 
 
 int transpose2d(rsvdb_ctx* c, const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows, int64_t cols) {
   if (rows <= 0 || cols <= 0) return 0;
-  dim3 g((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
-  k_transpose<<<g, dim3(32, 8), 0, c->stream>>>(src, lds, dst, ldd, (int)rows, (int)cols);
-  RSVDB_CUDA(c, cudaGetLastError());
-  ++c->launches;
+  const int64_t cblocks = (cols + 31) / 32;
+  for (int64_t cb = 0; cb < cblocks; cb += 65535) {                      // gridDim.y is limited to 65535
+    dim3 g((unsigned)((rows + 31) / 32), (unsigned)std::min<int64_t>(65535, cblocks - cb));
+    k_transpose<<<g, dim3(32, 8), 0, c->stream>>>(src, lds, dst, ldd, rows, cols, cb);
+    RSVDB_CUDA(c, cudaGetLastError());
+    ++c->launches;
+  }
   return 0;
 }
 
@@ -139,7 +143,23 @@ static int qr_wide(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bo
 }
 
 int qr_inplace(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bool sharded, const double** R) {
-  if (l > QR_FAST_MAX && rows >= 4 * (int64_t)l) return qr_wide(c, Y, rows, l, ldy, sharded, R);
+  if (l > QR_FAST_MAX) {
+    // The wide path and the plain TSQR issue different collective sequences, so with row shards every rank must take
+    // the same branch although shard heights differ by one row (reference split rule): the ranks agree on the SHORTEST
+    // shard first (one 8-byte all-reduce; only panels wider than the shared-memory TSQR get here).
+    int64_t rows_min = rows;
+    if (sharded && c->nranks > 1) {
+      RSVDB_CUDA(c, c->svd_ws.reserve(64));
+      const double neg = -(double)rows;                                    // min(rows) = -max(-rows); exact in FP64
+      RSVDB_CUDA(c, cudaMemcpyAsync(c->svd_ws.ptr, &neg, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      RSVDB_TRY(comm_allreduce_max(c, c->svd_ws.ptr, 1));
+      double got = 0.0;
+      RSVDB_CUDA(c, cudaMemcpyAsync(&got, c->svd_ws.ptr, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      RSVDB_CUDA(c, cudaStreamSynchronize(c->stream));
+      rows_min = (int64_t)(-got);
+    }
+    if (rows_min >= 4 * (int64_t)l) return qr_wide(c, Y, rows, l, ldy, sharded, R);
+  }
   PhaseTimer pt(c, PH_QR);
   int k = 0;
   Tsqr t(&c->qr_ws, c->side_stream, c->side_ev);
@@ -214,7 +234,7 @@ static int gemm_at_phase(rsvdb_ctx* c, const double* A, int64_t K, int64_t M, in
   if (reduce && c->nranks > 1) {
     // A^T Q = sum over row shards of A_p^T Q_p; Z is contiguous (ldz == M or N) by construction in this file
     PhaseTimer pc(c, PH_COMM);
-    RSVDB_TRY(comm_allreduce_sum(c, Z, (size_t)M * N));
+    RSVDB_TRY(comm_allreduce_sum(c, Z, transpose_out ? (size_t)ldz * M : (size_t)ldz * N));   // padding rows ride along
   }
   return 0;
 }
@@ -248,8 +268,9 @@ static int upload_and_first_pass(rsvdb_ctx* c, double* A, int64_t m, int64_t n, 
 int range_finder(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
                  int l, int q, double* Q, int64_t ldq, const HostUpload* up, const Centering* cen) {
   if (l <= 0 || q < 0) return fail(c, -1, "range_finder: l must be positive and q non-negative");
-  // Z (n x l) lives in tmp_ws at offset 0
-  RSVDB_CUDA(c, c->tmp_ws.reserve(std::max<size_t>(c->tmp_ws.bytes, (size_t)n * l * sizeof(double))));
+  // Z (n x l, even leading dimension: TMA needs 16-byte column strides) lives in tmp_ws at offset 0
+  const int64_t ldz = even_ld(n);
+  RSVDB_CUDA(c, c->tmp_ws.reserve(std::max<size_t>(c->tmp_ws.bytes, (size_t)ldz * l * sizeof(double))));
   double* Z = c->tmp_ws.ptr;
   if (cen && c->pca_ws.bytes < PcaScratch::total(n, l) * sizeof(double))
     return fail(c, -1, "range_finder: reserve pca_ws (PcaScratch::total) before building a Centering");
@@ -261,9 +282,9 @@ int range_finder(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t ld
   }
   RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));                       // Q = qr(Y).Q            :60-61
   for (int it = 0; it < q; ++it) {                                             // :62
-    RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, ldq, l, Z, n, 0, true, cen));  // Y = A^T * Q            :63
-    RSVDB_TRY(qr_inplace(c, Z, n, l, n, false, nullptr));                      // Q = qr(Y).Q  (n x l)   :64-65
-    RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Z, n, l, Q, ldq, cen));           // Y = A * Q              :66
+    RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, ldq, l, Z, ldz, 0, true, cen));// Y = A^T * Q            :63
+    RSVDB_TRY(qr_inplace(c, Z, n, l, ldz, false, nullptr));                    // Q = qr(Y).Q  (n x l)   :64-65
+    RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Z, ldz, l, Q, ldq, cen));         // Y = A * Q              :66
     RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));                     // Q = qr(Y).Q            :67-68
   }
   return 0;
@@ -315,23 +336,25 @@ int rsvd_device(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda
   if (method != 0 && method != 1 && method != 2) return fail(c, -1, "Unsupported SVD method");   // src/rSVD.cpp:122-123
   if (l <= 0 || n <= 0 || m < 0) return fail(c, -1, "rSVD: bad shape");
   const int64_t k = std::min<int64_t>(l, n);
-  // tmp_ws layout: [Z / Bt : n x l][Q : m x l][Ut : l x k]
-  const size_t need = ((size_t)n * l + (size_t)m * l + (size_t)l * l + 64) * sizeof(double);
+  // tmp_ws layout: [Z / Bt : n x l][Q : m x l][Ut : l x k]; even leading dimensions and even offsets keep every
+  // sub-buffer TMA-addressable (16-byte base and column stride) whatever the parity of m, n and l
+  const int64_t ldz = even_ld(n), ldq = even_ld(m), ldut = even_ld(l);
+  const size_t need = ((size_t)ldz * l + (size_t)ldq * l + (size_t)ldut * l + 64) * sizeof(double);
   RSVDB_CUDA(c, c->tmp_ws.reserve(need));
   double* Bt = c->tmp_ws.ptr;
-  double* Q = Bt + (size_t)n * l;
-  double* Ut = Q + (size_t)m * l;
-  RSVDB_TRY(range_finder(c, A, m, n, lda, Omega, ldo, l, q, Q, m, up, cen));        // Stage A          src/rSVD.cpp:84-85
-  RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, m, l, Bt, n, 0, true, cen));          // B^T = A^T Q      :89 (stored transposed)
+  double* Q = Bt + (size_t)ldz * l;
+  double* Ut = Q + (size_t)ldq * l;
+  RSVDB_TRY(range_finder(c, A, m, n, lda, Omega, ldo, l, q, Q, ldq, up, cen));      // Stage A          src/rSVD.cpp:84-85
+  RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, ldq, l, Bt, ldz, 0, true, cen));      // B^T = A^T Q      :89 (stored transposed)
   if (method == 1) {
-    RSVDB_TRY(small_svd_power_t(c, Bt, n, l, n, 0, seed, Ut, l, l, S, V, ldv, nullptr));   // SVD<Power>(B)    :105-112
+    RSVDB_TRY(small_svd_power_t(c, Bt, ldz, l, n, 0, seed, Ut, ldut, l, S, V, ldv, nullptr));   // SVD<Power>(B)    :105-112
   } else {
-    RSVDB_TRY(small_svd_jacobi(c, nullptr, 0, Bt, n, l, n, Ut, l, S, V, ldv));       // SVD<method>(B)   :96-121
+    RSVDB_TRY(small_svd_jacobi(c, nullptr, 0, Bt, ldz, l, n, Ut, ldut, S, V, ldv));  // SVD<method>(B)   :96-121
   }
   {
     PhaseTimer pt(c, PH_OTHER);                                                      // U = Q * Utilde   :128
     int nl = 0;
-    RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, Q, m, l, m, Ut, l, (int)k, U, ldu, &nl));
+    RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, Q, m, l, ldq, Ut, ldut, (int)k, U, ldu, &nl));
     c->launches += nl;
   }
   return 0;

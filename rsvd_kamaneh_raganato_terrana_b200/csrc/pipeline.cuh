@@ -6,6 +6,9 @@
 
 namespace rsvdb {
 
+// smallest even leading dimension >= rows (TMA needs 16-byte column strides)
+inline int64_t even_ld(int64_t rows) { return rows < 2 ? 2 : ((rows + 1) & ~int64_t(1)); }
+
 // Orthonormalise the columns of Y (rows x l, ldy) in place with Householder TSQR.  sharded: Y is this rank's row block of
 // a panel distributed over c->nranks ranks.  *R (optional) receives a device pointer to the l x l upper-triangular factor
 // (leading dimension l), valid until the next QR on this context.

@@ -66,13 +66,18 @@ __global__ void k_pm_mx(const double* __restrict__ Mt, int64_t ldmt, int64_t cdi
 __global__ void k_pm_mty(const double* __restrict__ Mt, int64_t ldmt, int64_t cdim, int r, const double* __restrict__ y,
                          double* __restrict__ z, double* __restrict__ partial, const int* stop) {
   __shared__ double red[32];
-  extern __shared__ double ys[];
+  constexpr int YT = 2048;                       // y is staged through shared memory in fixed tiles: any r launches
+  __shared__ double ys[YT];
   if (*stop) return;
-  for (int i = threadIdx.x; i < r; i += blockDim.x) ys[i] = y[i];
-  __syncthreads();
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double acc = 0.0;
-  if (j < cdim) for (int i = 0; i < r; ++i) acc = fma(Mt[(size_t)i * ldmt + j], ys[i], acc);
+  for (int i0 = 0; i0 < r; i0 += YT) {
+    const int nt = min(YT, r - i0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) ys[i] = y[i0 + i];
+    __syncthreads();
+    if (j < cdim) for (int i = 0; i < nt; ++i) acc = fma(Mt[(size_t)(i0 + i) * ldmt + j], ys[i], acc);
+  }
   if (j < cdim) z[j] = acc;
   const double s = block_sum(acc * acc, red);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
@@ -127,6 +132,7 @@ int pm_iterations(int64_t ncols) {   // src/PM.cpp:25-28
 int small_svd_power_t(rsvdb_ctx* c, double* Mt, int64_t ldmt, int64_t r, int64_t cdim, int rdim, uint64_t seed,
                       double* U, int64_t ldu, int u_cols, double* S, double* V, int64_t ldv, int* found_host) {
   PhaseTimer pt(c, PH_SMALL_SVD);
+  c->d_svd_info = nullptr;                  // no Jacobi sweep count belongs to this call
   const int64_t kmin = std::min(r, cdim);
   const int dim = rdim ? rdim : (int)kmin;
   if (dim > kmin) return fail(c, -1, "SVD<Power>: r larger than min(rows, cols)");
@@ -147,7 +153,7 @@ int small_svd_power_t(rsvdb_ctx* c, double* Mt, int64_t ldmt, int64_t r, int64_t
     double* cur = x; double* nxt = z;
     for (int it = 0; it < s; ++it) {
       k_pm_mx<<<(int)r, threads, 0, st>>>(Mt, ldmt, cdim, cur, partial, nb, y, flags);
-      k_pm_mty<<<nb, threads, r * sizeof(double), st>>>(Mt, ldmt, cdim, (int)r, y, nxt, partial, flags);
+      k_pm_mty<<<nb, threads, 0, st>>>(Mt, ldmt, cdim, (int)r, y, nxt, partial, flags);
       std::swap(cur, nxt);
     }
     double* vcol = V + (size_t)i * ldv;

@@ -12,6 +12,7 @@
 // by the same kernel, recursively, until one leaf remains.  Q is then formed top-down: the CTA of leaf b applies its
 // reflectors to [C_b; 0], where C_b is the b-th l x l block of the explicit Q of the level above (identity at the
 // top, or -- multi-GPU -- this rank's block of the Q of the all-gathered R factors).
+#include "dev_once.cuh"
 #include "tsqr.cuh"
 
 #include <algorithm>
@@ -890,8 +891,8 @@ int cl_max_nodes() { static int m = -1; if (m < 0) { const char* e = getenv("RSV
 size_t blk_smem_bytes(int l) { return ((size_t)(l + 8) * (256 + 4) + 64 + 720 + (size_t)l) * sizeof(double); }
 
 cudaError_t set_attr_blk_once() {
-  static bool done = false;
-  if (done) return cudaSuccess;
+  static DevOnce done;
+  if (done.get()) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(k_house_apply_blk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_house_factor_la<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -900,18 +901,18 @@ cudaError_t set_attr_blk_once() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_node_apply_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  done = true;
+  done.set();
   return cudaSuccess;
 }
 
 template <int BR> cudaError_t set_attr_once() {
-  static bool done = false;
-  if (done) return cudaSuccess;
+  static DevOnce done;
+  if (done.get()) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(k_house_factor<BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_house_apply<BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  done = true;
+  done.set();
   return cudaSuccess;
 }
 
@@ -1058,9 +1059,9 @@ cudaError_t Tsqr::form_q(cudaStream_t st, double* Y, long long ldy, const double
         e = launch_apply(up_sc, false, nullptr, 0); if (e != cudaSuccess) return e;
       }
       // (B) chain top-down: E_i[node b] = N_i[node b] * E_{i+1}[rows b*l .. (b+1)*l)   (E_top = N_top * Ctop)
-      static bool ng_attr = false;
+      static DevOnce ng_attr;
       const size_t ng_smem = ((size_t)l_ * l_ + (size_t)l_ * (NG_ROWS + 1)) * sizeof(double);
-      if (!ng_attr) { e = cudaFuncSetAttribute(k_node_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; ng_attr = true; }
+      if (!ng_attr.get()) { e = cudaFuncSetAttribute(k_node_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; ng_attr.set(); }
       const double* Epar = Ctop; long long ldpar = ldc;
       for (int i = nlev - 1; i >= 1; --i) {
         double* V; long long ldv; level_V(i, &V, &ldv);
