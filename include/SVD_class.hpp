@@ -3,6 +3,25 @@
 #ifndef SVD_CLASS_HPP
 #define SVD_CLASS_HPP
 
+// the standard headers the reference's SVD_class.hpp pulls in for its callers (include/SVD_class.hpp:4-21), so that
+// callers relying on those transitive includes (PCA/tests/pca_test.cpp uses std::ifstream and MPI_Init through it) compile unchanged
+#include <algorithm>
+#include <cmath>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <queue>
+#include <sstream>
+#include <string>
+#include <tuple>
+#include <vector>
+#if defined(__has_include)
+#if __has_include(<mpi.h>)
+#include <mpi.h>
+#endif
+#endif
+
 #include "rsvdb_dense.hpp"
 #include "JacobiOperations.hpp"
 #include "Jacobi_Class.hpp"

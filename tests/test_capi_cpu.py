@@ -66,3 +66,18 @@ def test_cpp_dropin_headers_compile_and_link():
     for h in ("rSVD.hpp", "SVD_class.hpp", "QR.hpp", "PM.hpp", "Jacobi_Class.hpp", "JacobiOperations.hpp", "matrixOperations.hpp", "PCA_class.hpp", "POD.hpp",
               "image_compression/rSVD.hpp", "image_compression/SVD.hpp", "image_compression/PowerMethod.hpp", "image_compression/QR.hpp", "image_compression/image_comp.hpp"):
         assert (ROOT / "include" / h).exists(), h
+
+
+def test_reference_mains_compile_unmodified_over_dropin_headers():
+    """The reference's own tests/rSVD_test.cpp, svd_test.cpp, QRTest.cpp, rSVD_test2.cpp, PCA/tests/*.cpp and POD.cpp build, unchanged,
+    with -I include first (tests/cpp/Makefile).  Compile-and-link only on the CPU box; tests/test_gpu_parity.py runs them."""
+    import subprocess
+    from pathlib import Path
+    import pytest
+    root = Path(__file__).resolve().parent.parent
+    if not Path("/root/reference/tests").is_dir():
+        pytest.skip("/root/reference is not present on this box")
+    r = subprocess.run(["make", "-B", "-C", str(root / "tests" / "cpp"), "refmains"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for name in ("rSVD_test", "svd_test", "QRTest", "rSVD_test2", "pca_test", "athletic_test", "pod_ref_class"):
+        assert (root / "tests" / "cpp" / "_refbin" / name).exists(), name
