@@ -17,6 +17,11 @@ typedef int MPI_Datatype;
 inline const double*& oracle_mpi_override_ptr() { static const double* p = nullptr; return p; }
 inline std::size_t& oracle_mpi_override_count() { static std::size_t n = 0; return n; }
 inline void oracle_mpi_set_bcast_override(const double* p, std::size_t count) { oracle_mpi_override_ptr() = p; oracle_mpi_override_count() = count; }
+struct MPI_Status { int MPI_SOURCE, MPI_TAG, MPI_ERROR; };
+#define MPI_INT 4
+// point-to-point calls only appear on multi-rank branches (image_compression/src/image_com.cpp:387,400); with one rank they are unreachable
+inline int MPI_Send(const void*, int, MPI_Datatype, int, int, MPI_Comm) { return MPI_SUCCESS; }
+inline int MPI_Recv(void*, int, MPI_Datatype, int, int, MPI_Comm, MPI_Status*) { return MPI_SUCCESS; }
 inline int MPI_Init(int*, char***) { return MPI_SUCCESS; }
 inline int MPI_Finalize() { return MPI_SUCCESS; }
 inline int MPI_Comm_rank(MPI_Comm, int* r) { *r = 0; return MPI_SUCCESS; }

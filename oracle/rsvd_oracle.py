@@ -57,6 +57,10 @@ def build(force: bool = False) -> Path:
     drv = _HERE / "ref_driver.cpp"
     if Path("/root/reference/src").is_dir() and (force or not ref_so.exists() or ref_so.stat().st_mtime < drv.stat().st_mtime):
         subprocess.run(["make", "-C", str(_HERE), "ref"], check=True, capture_output=True)
+    ref1_so = _HERE / "_ref" / "libref_imgcomp.so"
+    drv1 = _HERE / "ref_driver_v1.cpp"
+    if Path("/root/reference/image_compression/src").is_dir() and (force or not ref1_so.exists() or ref1_so.stat().st_mtime < drv1.stat().st_mtime):
+        subprocess.run(["make", "-C", str(_HERE), "ref_v1"], check=True, capture_output=True)
     return so
 
 
@@ -132,14 +136,17 @@ def svd_parallel_jacobi(B):
     return U, S, V, {"passes": int(passes), "rotations": int(rot.value)}
 
 
-def svd_power(B, r: int = 0, seed: int = 0):
+def svd_power(B, r: int = 0, seed: int = 0, resize: bool = True):
     """include/SVD_class.hpp:184-219 + src/PM.cpp:4-81.  Start vectors come from a seeded generator (the reference uses
-    std::random_device).  Returns (U m x m [or m x found on early exit], S, V n x n with singular vectors in ROWS)."""
+    std::random_device).  Returns (U m x m [or m x found on early exit], S, V n x n with singular vectors in ROWS).
+    resize=False: the OLDER API's singularValueDecomposition (image_compression/src/SVD.cpp:30-55) has no sigma < 1e-12 early
+    exit and never resizes its outputs; for it the triplets past the numerical rank are left at their initial values
+    (identity columns / rows, sigma 0) -- the reference computes rounding noise there (sigma ~ 1e-16)."""
     B = _f(B); m, n = B.shape; k = min(m, n); dim = r if r else k
     starts = _f(np.random.default_rng(seed).standard_normal((n, dim)))
     U = np.zeros((m, m), order="F"); S = np.zeros(k); V = np.zeros((n, n), order="F")
     found = int(_lib().oc_power_svd(_p(B), ctypes.c_long(m), ctypes.c_long(n), ctypes.c_int(r), _p(starts), _p(U), _p(S), _p(V)))
-    if found < dim:    # conservativeResize on early exit, :198-209
+    if found < dim and resize:    # conservativeResize on early exit, :198-209
         if found == 0:
             return np.zeros((m, 1), order="F"), np.zeros(1), np.zeros((n, 1), order="F"), {"found": 0}
         return _f(U[:, :found]), S[:found].copy(), _f(V[:, :found]), {"found": found}
@@ -190,8 +197,11 @@ def image_compress(A, k: int = -1, Omega=None, seed: int = 0):
     l = k + 10
     if Omega is None:
         Omega = np.random.default_rng(seed).standard_normal((n, l))
-    U, S, Vrows = rsvd(A, Omega, l, 1, POWER, seed)
-    return U, S, np.asfortranarray(Vrows[:l, :].T)          # the older API returns V with the vectors in columns
+    Q = intermediate_step(A, Omega, l, 1)                    # image_compression/src/rSVD.cpp:103-106 (q = 1)
+    B = Q.T @ A                                             # :109
+    Ut, S, Vrows, _ = svd_power(B, 0, seed, resize=False)   # singularValueDecomposition(B, S, Utilde, V, min_dim), :112-114
+    k = min(l, n)
+    return Q @ Ut[:, :k], S[:k], np.asfortranarray(Vrows[:k, :].T)   # :117; the older API returns V with the vectors in columns
 
 
 def image_reconstruct(U, S, V):
@@ -454,3 +464,64 @@ class RefLib:
         if rc != 0:
             raise ValueError("bad POD variant")
         return np.array(W[: dims[0] * dims[1]]).reshape((dims[0], dims[1]), order="F"), sigma[: dims[2]].copy()
+
+
+class RefLibV1:
+    """ctypes view of oracle/_ref/libref_imgcomp.so: the reference's OLDER API (image_compression/src/*.cpp) and its Image class,
+    compiled from the reference's own sources (oracle/ref_driver_v1.cpp)."""
+
+    def __init__(self):
+        so = _HERE / "_ref" / "libref_imgcomp.so"
+        if not so.exists():
+            build()
+        if not so.exists():
+            raise FileNotFoundError("oracle/_ref/libref_imgcomp.so is not built (needs /root/reference)")
+        self.lib = ctypes.CDLL(str(so))
+
+    @staticmethod
+    def available() -> bool:
+        return (_HERE / "_ref" / "libref_imgcomp.so").exists() or Path("/root/reference/image_compression/src").is_dir()
+
+    def intermediate_step(self, A, Omega, l, q=1):
+        A = _f(A); Omega = _f(Omega); m, n = A.shape
+        Q = np.zeros((m, l), order="F")
+        self.lib.ref1_intermediate_step(_p(A), ctypes.c_long(m), ctypes.c_long(n), _p(Omega), ctypes.c_int(l), ctypes.c_int(q), _p(Q))
+        return Q
+
+    def rsvd(self, A, l):
+        """rSVD(A, U, S, V, l): Omega is drawn inside from std::random_device -- not reproducible."""
+        A = _f(A); m, n = A.shape
+        U = np.zeros((m, l), order="F"); S = np.zeros(l); V = np.zeros(n * max(l, n)); dims = (ctypes.c_long * 5)()
+        self.lib.ref1_rsvd(_p(A), ctypes.c_long(m), ctypes.c_long(n), ctypes.c_int(l), _p(U), _p(S), _p(V), dims)
+        return U, S, np.array(V[: dims[3] * dims[4]]).reshape((dims[3], dims[4]), order="F")
+
+    def svd(self, A, dim):
+        A = _f(A); m, n = A.shape
+        S = np.zeros(dim); U = np.zeros((m, dim), order="F"); V = np.zeros((n, dim), order="F")
+        self.lib.ref1_svd(_p(A), ctypes.c_long(m), ctypes.c_long(n), ctypes.c_int(dim), _p(S), _p(U), _p(V))
+        return U, S, V
+
+    def power_method(self, A):
+        A = _f(A); m, n = A.shape
+        sigma = ctypes.c_double(); u = np.zeros(m); v = np.zeros(n)
+        self.lib.ref1_power_method(_p(A), ctypes.c_long(m), ctypes.c_long(n), ctypes.byref(sigma), _p(u), _p(v))
+        return sigma.value, u, v
+
+    def qr(self, A, reduced=True):
+        A = _f(A); m, n = A.shape
+        Q = np.zeros((m, n if reduced else m), order="F"); R = np.zeros((n if reduced else m, n), order="F")
+        self.lib.ref1_qr(_p(A), ctypes.c_long(m), ctypes.c_long(n), ctypes.c_int(int(reduced)), _p(Q), _p(R))
+        return Q, R
+
+    def image_flow(self, path, rows, cols, scale, k):
+        """Image: load -> downscale(scale) -> normalize -> compress(k) -> reconstruct.  rows x cols: the matrix shape the class
+        will hold (width/scale x height/scale).  Returns dict(norm, lo, hi, S, recon, ratio, l)."""
+        l = k + 10
+        norm = np.zeros((rows, cols), order="F"); recon = np.zeros((rows, cols), order="F"); S = np.zeros(l)
+        lo = ctypes.c_double(); hi = ctypes.c_double(); ratio = ctypes.c_double(); dims = (ctypes.c_long * 3)()
+        rc = self.lib.ref1_image_flow(str(path).encode(), ctypes.c_int(scale), ctypes.c_int(k), _p(norm), ctypes.byref(lo), ctypes.byref(hi),
+                                      _p(S), _p(recon), ctypes.byref(ratio), dims)
+        if rc != 0:
+            raise IOError(f"Image::load failed for {path}")
+        assert (dims[0], dims[1], dims[2]) == (rows, cols, l), tuple(dims)
+        return dict(norm=norm, lo=lo.value, hi=hi.value, S=S, recon=recon, ratio=ratio.value, l=l)
