@@ -26,6 +26,7 @@ __device__ __forceinline__ double wsum(double v) {
 }
 
 constexpr int JMAX_RPL = 32;   // rows per lane of a 16-lane group: k <= 512
+int grid_min() { static int m = -1; if (m < 0) { const char* e = getenv("RSVDB_JACOBI_GRID_MIN"); m = e ? atoi(e) : 512; } return m; }
 
 // X, Z: k x k column-major with leading dimension k, in shared or global memory.
 // One column pair per HALF warp (16 lanes, RPL rows per lane): with 1024 threads all k/2 <= 64 pairs of a round-robin
@@ -317,12 +318,130 @@ k_jacobi_cl(const double* __restrict__ W, long long ldw, int k, int transpose_in
   jc_sync();                                        // peers may still be reading this CTA's shared memory
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Grid variant for factors that do not fit one SM (k > 512; the reference's SVD<Jacobi> / PCA<method> take any size,
+// include/SVD_class.hpp:101-180).  X and Z (k x k each) live in global memory and stay L2-resident (16 MB at k = 1000);
+// the k/2 disjoint column pairs of a round-robin step are independent, so one CTA rotates one pair and a step is one
+// launch.  Same rotation formula, threshold and epilogue as k_jacobi; the sweep count is read back once per sweep.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int JG_THREADS = 128;
+
+__global__ void k_jg_init(const double* __restrict__ W, long long ldw, int k, int transpose_in, double* __restrict__ X, double* __restrict__ Z) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)k * k) return;
+  const int i = (int)(e % k), j = (int)(e / k);
+  X[e] = transpose_in ? W[(size_t)i * ldw + j] : W[(size_t)j * ldw + i];
+  Z[e] = (i == j) ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(JG_THREADS)
+k_jg_step(double* __restrict__ X, double* __restrict__ Z, int k, int step, double tol2, int* __restrict__ rot) {
+  __shared__ double red[3][JG_THREADS / 32];
+  const int n = (k + 1) & ~1;
+  const int pi = blockIdx.x;
+  int p, q;
+  if (pi == 0) { p = n - 1; q = step; }
+  else { p = (step + pi) % (n - 1); q = (step - pi + (n - 1)) % (n - 1); }
+  if (p > q) { const int t = p; p = q; q = t; }
+  if (q >= k) return;                                   // the dummy player of an odd k
+  double* xp = X + (size_t)p * k; double* xq = X + (size_t)q * k;
+  double a = 0.0, b = 0.0, g = 0.0;
+  for (int i = threadIdx.x; i < k; i += JG_THREADS) {
+    const double vp = xp[i], vq = xq[i];
+    a = fma(vp, vp, a); b = fma(vq, vq, b); g = fma(vp, vq, g);
+  }
+  a = wsum(a); b = wsum(b); g = wsum(g);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = a; red[1][warp] = b; red[2][warp] = g; }
+  __syncthreads();
+  a = 0.0; b = 0.0; g = 0.0;
+#pragma unroll
+  for (int w = 0; w < JG_THREADS / 32; ++w) { a += red[0][w]; b += red[1][w]; g += red[2][w]; }   // same order in every thread
+  if (!(g * g > tol2 * (a * b) && fabs(g) > DBL_MIN)) return;
+  if (threadIdx.x == 0) atomicAdd(rot, 1);
+  const double d = b - a;
+  const double n2 = fma(d, d, 4.0 * g * g);
+  const double ir = rsqrt(n2);
+  const double c2 = fma(0.5 * fabs(d), ir, 0.5);
+  const double ic = rsqrt(c2);
+  const double c = c2 * ic;
+  const double s = ((d >= 0.0) ? g : -g) * ir * ic;
+  double* zp = Z + (size_t)p * k; double* zq = Z + (size_t)q * k;
+  for (int i = threadIdx.x; i < k; i += JG_THREADS) {
+    const double vp = xp[i], vq = xq[i];
+    xp[i] = c * vp - s * vq; xq[i] = s * vp + c * vq;
+    const double z1 = zp[i], z2 = zq[i];
+    zp[i] = c * z1 - s * z2; zq[i] = s * z1 + c * z2;
+  }
+}
+
+__global__ void k_jg_norms(const double* __restrict__ X, int k, double* __restrict__ sig) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= k) return;
+  double a = 0.0;
+  for (int i = lane; i < k; i += 32) a = fma(X[(size_t)j * k + i], X[(size_t)j * k + i], a);
+  a = wsum(a);
+  if (lane == 0) sig[j] = sqrt(a);
+}
+
+// rank sort (descending, ties by index) and the permuted write of U = X / sigma, Z  -- one CTA per column
+__global__ void __launch_bounds__(256)
+k_jg_finish(const double* __restrict__ X, const double* __restrict__ Z, const double* __restrict__ sig, int k, double* __restrict__ Uo, long long ldu,
+            double* __restrict__ So, double* __restrict__ Zo, long long ldz, int* __restrict__ info, int sweeps_signed, int rotations) {
+  __shared__ int cnt[8];
+  const int j = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double sj = sig[j];
+  int r = 0;
+  for (int i = threadIdx.x; i < k; i += 256) { const double si = sig[i]; r += (si > sj || (si == sj && i < j)) ? 1 : 0; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  if (lane == 0) cnt[warp] = r;
+  __syncthreads();
+  r = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) r += cnt[w];
+  const double inv = (sj > 0.0) ? 1.0 / sj : 0.0;
+  if (threadIdx.x == 0) So[r] = sj;
+  for (int i = threadIdx.x; i < k; i += 256) {
+    Uo[(size_t)r * ldu + i] = (sj > 0.0) ? X[(size_t)j * k + i] * inv : (i == j ? 1.0 : 0.0);
+    Zo[(size_t)r * ldz + i] = Z[(size_t)j * k + i];
+  }
+  if (j == 0 && threadIdx.x == 0 && info) { info[0] = sweeps_signed; info[1] = rotations; }
+}
+
+cudaError_t jacobi_svd_grid(GemmWorkspace& ws, cudaStream_t st, const double* W, long long ldw, int k, int transpose_in,
+                            double* U, long long ldu, double* S, double* Z, long long ldz, int* d_info, int max_sweeps, int* launches) {
+  const size_t kk = (size_t)k * k;
+  cudaError_t e = ws.reserve((2 * kk + k + 16) * sizeof(double)); if (e != cudaSuccess) return e;
+  double* X = ws.ptr; double* Zw = X + kk; double* sig = Zw + kk; int* rot = reinterpret_cast<int*>(sig + k);
+  k_jg_init<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(W, ldw, k, transpose_in, X, Zw);
+  const int n = (k + 1) & ~1, npairs = n >> 1;
+  const double tol = sqrt((double)k) * (0.5 * DBL_EPSILON);
+  int sweep = 0, total = 0, nl = 1; bool converged = (k < 2);
+  while (!converged && sweep < max_sweeps) {
+    e = cudaMemsetAsync(rot, 0, sizeof(int), st); if (e != cudaSuccess) return e;
+    for (int step = 0; step < n - 1; ++step) k_jg_step<<<npairs, JG_THREADS, 0, st>>>(X, Zw, k, step, tol * tol, rot);
+    nl += n - 1;
+    int h = 0;
+    e = cudaMemcpyAsync(&h, rot, sizeof(int), cudaMemcpyDeviceToHost, st); if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st); if (e != cudaSuccess) return e;       // one read-back per sweep decides whether another sweep is needed
+    ++sweep; total += h; converged = (h == 0);
+  }
+  k_jg_norms<<<(k + 7) / 8, 256, 0, st>>>(X, k, sig);
+  k_jg_finish<<<k, 256, 0, st>>>(X, Zw, sig, k, U, ldu, S, Z, ldz, d_info, converged ? sweep : -sweep, total);
+  nl += 2;
+  if (launches) *launches += nl;
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t jacobi_svd_square(GemmWorkspace& ws, cudaStream_t st, const double* W, long long ldw, int k, int transpose_in,
                               double* U, long long ldu, double* S, double* Z, long long ldz, int* d_info, int* launches) {
   if (k <= 0) return cudaSuccess;
-  if (k > 16 * JMAX_RPL) return cudaErrorInvalidValue;
+  // beyond one SM's reach (k > 512) -- and already above k = grid_min(), where the single-CTA global-memory loop is slower --
+  // the pairs of a step are spread over the grid
+  if (k > grid_min()) return jacobi_svd_grid(ws, st, W, ldw, k, transpose_in, U, ldu, S, Z, ldz, d_info, 60, launches);
   {
     const int sr = (k + JC - 1) / JC, npairs = ((k + 1) & ~1) >> 1;
     const size_t cl_smem = (2 * (size_t)k * sr + 2 * (size_t)npairs * JC * 4 + (size_t)k * JC + k) * sizeof(double);

@@ -295,7 +295,7 @@ int small_svd_jacobi(rsvdb_ctx* c, const double* M, int64_t ldm, const double* M
   PhaseTimer pt(c, PH_SMALL_SVD);
   const int64_t k = std::min(r, cd);
   if (k <= 0) return 0;
-  if (k > 512) return fail(c, -6, "small SVD: min(rows, cols) > 512 is not supported");
+  if (k > 32768) return fail(c, -6, "SVD<Jacobi>: min(rows, cols) > 32768 is not supported (two k x k work matrices must fit in device memory)");
   int nl = 0;
   // scratch: tall copy (max(r,cd) x k), Uw (k x k), Zw (k x k), info
   const int64_t tall = std::max(r, cd);
