@@ -462,12 +462,11 @@ cudaError_t jacobi_svd_square(GemmWorkspace& ws, cudaStream_t st, const double* 
   }
   const size_t smem_need = (2 * (size_t)k * k + k) * sizeof(double);
   const int use_smem = smem_need <= 220 * 1024;
+  // neither one SM's nor a 4-CTA cluster's shared memory holds the factor (k > ~116): measured, the grid variant beats a single
+  // CTA looping over global memory by 6x at k = 256 and 19x at k = 512 (profiles/r02_jacobi_grid.log)
+  if (!use_smem) return jacobi_svd_grid(ws, st, W, ldw, k, transpose_in, U, ldu, S, Z, ldz, d_info, 60, launches);
   double* Xg = nullptr; double* Zg = nullptr;
-  if (!use_smem) {
-    cudaError_t e = ws.reserve(smem_need + 64); if (e != cudaSuccess) return e;
-    Xg = ws.ptr; Zg = ws.ptr + (size_t)k * k;
-  }
-  const size_t smem = use_smem ? smem_need : 0;
+  const size_t smem = smem_need;
   const int threads = k >= 48 ? 1024 : (k >= 24 ? 512 : 256);
   const int rpl = (k + 15) / 16;
 #define JLAUNCH(R)                                                                                                   \
@@ -475,8 +474,7 @@ cudaError_t jacobi_svd_square(GemmWorkspace& ws, cudaStream_t st, const double* 
     if (!attr.get()) { cudaError_t e = cudaFuncSetAttribute(k_jacobi<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
                  if (e != cudaSuccess) return e; attr.set(); }                                                      \
     k_jacobi<R><<<1, threads, smem, st>>>(W, ldw, k, transpose_in, U, ldu, S, Z, ldz, Xg, Zg, use_smem, 60, d_info); }
-  if (rpl <= 1) JLAUNCH(1) else if (rpl <= 2) JLAUNCH(2) else if (rpl <= 4) JLAUNCH(4) else if (rpl <= 7) JLAUNCH(7) else if (rpl <= 8) JLAUNCH(8)
-  else if (rpl <= 16) JLAUNCH(16) else JLAUNCH(32)
+  if (rpl <= 1) JLAUNCH(1) else if (rpl <= 2) JLAUNCH(2) else if (rpl <= 4) JLAUNCH(4) else if (rpl <= 7) JLAUNCH(7) else JLAUNCH(8)
 #undef JLAUNCH
   if (launches) ++*launches;
   return cudaGetLastError();

@@ -167,7 +167,9 @@ int rsvd_csr_device(rsvdb_ctx* c, int64_t m, int64_t n, int64_t nnz, const int64
   const int64_t k = std::min<int64_t>(l, n);
   const int64_t big = std::max(m, n);
   // tmp_ws: [Bt n x l][Q m x l][Ut l x l][R1 big x l (row-major staging)][R2 big x l][transposed CSR]
-  const size_t d_bt = (size_t)n * l, d_q = (size_t)m * l, d_ut = (size_t)l * l + 64, d_r = (size_t)big * l + 64;
+  // even leading dimensions / offsets: the dense products on Q and Bt stay on the TMA + DMMA path for odd m, n, l
+  const int64_t ldb = even_ld(n), ldq = even_ld(m), ldut = even_ld(l);
+  const size_t d_bt = (size_t)ldb * l, d_q = (size_t)ldq * l, d_ut = (size_t)ldut * l + 64, d_r = (((size_t)big * l + 1) & ~size_t(1)) + 64;
   const size_t d_rowptrT = (size_t)n + 2, d_colT = ((size_t)nnz + 1) / 2 + 2, d_valT = (size_t)nnz + 2;
   RSVDB_CUDA(c, c->tmp_ws.reserve((d_bt + d_q + d_ut + 2 * d_r + d_rowptrT + d_colT + d_valT) * sizeof(double)));
   double* Bt = c->tmp_ws.ptr; double* Q = Bt + d_bt; double* Ut = Q + d_q; double* R1 = Ut + d_ut; double* R2 = R1 + d_r;
@@ -191,24 +193,24 @@ int rsvd_csr_device(rsvdb_ctx* c, int64_t m, int64_t n, int64_t nnz, const int64
       RSVDB_TRY(csr_spmm_rm(c, n, rowptrT, colT, valT, R1, l, R2));
       RSVDB_TRY(transpose2d(c, R2, l, Zcm, ldz, l, n));
     }
-    if (c->nranks > 1) { PhaseTimer pc(c, PH_COMM); RSVDB_TRY(comm_allreduce_sum(c, Zcm, (size_t)n * l)); }
+    if (c->nranks > 1) { PhaseTimer pc(c, PH_COMM); RSVDB_TRY(comm_allreduce_sum(c, Zcm, (size_t)ldz * l)); }
     return 0;
   };
-  RSVDB_TRY(spmm_a(Omega, ldo, Q, m));                                // Y = A * Omega                  src/rSVD.cpp:59
-  RSVDB_TRY(qr_inplace(c, Q, m, l, m, true, nullptr));                // :60-61
+  RSVDB_TRY(spmm_a(Omega, ldo, Q, ldq));                              // Y = A * Omega                  src/rSVD.cpp:59
+  RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));              // :60-61
   for (int it = 0; it < q; ++it) {
-    RSVDB_TRY(spmm_at(Q, m, Bt, n));                                  // Y = A^T * Q                    :63
-    RSVDB_TRY(qr_inplace(c, Bt, n, l, n, false, nullptr));            // :64-65
-    RSVDB_TRY(spmm_a(Bt, n, Q, m));                                   // Y = A * Q                      :66
-    RSVDB_TRY(qr_inplace(c, Q, m, l, m, true, nullptr));              // :67-68
+    RSVDB_TRY(spmm_at(Q, ldq, Bt, ldb));                              // Y = A^T * Q                    :63
+    RSVDB_TRY(qr_inplace(c, Bt, n, l, ldb, false, nullptr));          // :64-65
+    RSVDB_TRY(spmm_a(Bt, ldb, Q, ldq));                               // Y = A * Q                      :66
+    RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));            // :67-68
   }
-  RSVDB_TRY(spmm_at(Q, m, Bt, n));                                    // B^T = A^T Q                    :89
-  if (method == 1) { RSVDB_TRY(small_svd_power_t(c, Bt, n, l, n, 0, seed, Ut, l, l, S, V, ldv, nullptr)); }
-  else { RSVDB_TRY(small_svd_jacobi(c, nullptr, 0, Bt, n, l, n, Ut, l, S, V, ldv)); }
+  RSVDB_TRY(spmm_at(Q, ldq, Bt, ldb));                                // B^T = A^T Q                    :89
+  if (method == 1) { RSVDB_TRY(small_svd_power_t(c, Bt, ldb, l, n, 0, seed, Ut, ldut, l, S, V, ldv, nullptr)); }
+  else { RSVDB_TRY(small_svd_jacobi(c, nullptr, 0, Bt, ldb, l, n, Ut, ldut, S, V, ldv)); }
   {
     PhaseTimer pt(c, PH_OTHER);
     int nl = 0;
-    RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, Q, m, l, m, Ut, l, (int)k, U, ldu, &nl));   // U = Q * Utilde  :128
+    RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, Q, m, l, ldq, Ut, ldut, (int)k, U, ldu, &nl));   // U = Q * Utilde  :128
     c->launches += nl;
   }
   return 0;
