@@ -14,6 +14,7 @@
 // top, or -- multi-GPU -- this rank's block of the Q of the all-gathered R factors).
 #include "dev_once.cuh"
 #include "tsqr.cuh"
+#include "ptx.cuh"
 
 #include <algorithm>
 #include <cfloat>

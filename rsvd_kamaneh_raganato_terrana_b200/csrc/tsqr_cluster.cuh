@@ -32,6 +32,24 @@ __device__ __forceinline__ double ld_cluster(const double* p, unsigned rank) {
   return v;
 }
 
+// Remote store + completion signal in one operation: the 8-byte value lands in CTA `rank`'s copy of *p and 8 bytes are
+// credited to that CTA's copy of *bar (complete_tx).  Lets the panel teams of a cluster exchange their per-reflector partial
+// sums without a hardware cluster barrier (which every thread of every CTA would have to join).
+__device__ __forceinline__ void st_async_cluster(double* p, unsigned rank, double v, uint64_t* bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(map_cluster(p, rank)), "l"(__double_as_longlong(v)), "r"(map_cluster(bar, rank)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+
 // clean reflector value V[grow][r] of the panel at column / node row c0; grow = node row index of local row `lrow`
 __device__ __forceinline__ double clean_v_cl(const double* S, const double* Vtop, int c0, int grow, int lrow, int r) {
   constexpr int LDS = 256 + 4;
@@ -46,8 +64,11 @@ constexpr int CLS_RED = 0, CLS_DROW = 64, CLS_XCH = 72, CLS_GTOT = CLS_XCH + 2 *
 
 // All CTAs of the cluster factor the panel [c0, c0+pb) together.  Every thread of every CTA must call this (non-row
 // warps only take part in the cluster barriers).  Outputs as panel_factor_la; T / tau are identical in all CTAs.
+// Per reflector the 8 column products (+ the diagonal row, from rank 0) of every CTA go to every CTA with st.async and are
+// awaited on a local mbarrier by the row team only (xbar[2], alternating per reflector; xphase tracks their parities): ncu
+// showed barrier.cluster per reflector -- 2048 threads arriving 100 times per node -- as the top stall of the round-1 kernel.
 __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double* Tsm, double* tau_s, double* Tglob, double* sc,
-                                                int c0, int pb, int warp, int lane, unsigned rank) {
+                                                int c0, int pb, int warp, int lane, unsigned rank, uint64_t* xbar, uint32_t& xphase) {
   constexpr int LDS = 256 + 4;
   double* red = sc + CLS_RED; double* drow = sc + CLS_DROW; double* xch = sc + CLS_XCH; double* Gtot = sc + CLS_GTOT;
   double* Gs = sc + CLS_XW;                      // [8 warps][64] during the Gram step
@@ -78,6 +99,7 @@ __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double*
           for (int c = 0; c < 8; ++c) drow[c] = a[c];
         }
         bar_rows();
+        if (warp == 0 && lane == 0) mbar_expect_tx(&xbar[b], CL * 16 * 8);   // this round: 16 doubles from each CTA of the cluster
         if (warp == 0 && lane < 16) {            // CTA partial (8 column products) + the diagonal row (from rank 0) to every CTA
           double v;
           if (lane < 8) { v = 0.0;
@@ -86,10 +108,11 @@ __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double*
           } else v = (rank == 0) ? drow[lane - 8] : 0.0;
           double* slot = xch + b * 16 * CL + lane * CL + rank;
 #pragma unroll
-          for (unsigned tr = 0; tr < CL; ++tr) st_cluster(slot, tr, v);
+          for (unsigned tr = 0; tr < CL; ++tr) st_async_cluster(slot, tr, v, &xbar[b]);
         }
+        mbar_wait_cluster(&xbar[b], (xphase >> b) & 1u);
+        xphase ^= (1u << b);
       }
-      cluster_sync_all();
       if (!roww) continue;
       double tot[8];
 #pragma unroll
@@ -276,6 +299,8 @@ k_node_factor_cl(double* __restrict__ Y, long long ldy, long long rows, int l, d
   double* Tsm = Vtop + 64;                         // 64
   double* sc = Tsm + 64;                           // CLS_TOTAL
   double* tau_s = sc + CLS_TOTAL;
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(tau_s + l);     // 2 mbarriers of the per-reflector exchange
+  uint32_t xphase = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned rank = cluster_rank();
   const int node = blockIdx.x / CL;
@@ -287,11 +312,13 @@ k_node_factor_cl(double* __restrict__ Y, long long ldy, long long rows, int l, d
     const double* src = Y + (size_t)k * ldy + r0;
     for (int i = lane; i < 256; i += 32) S[(size_t)k * LDS + i] = (i < nrows) ? src[i] : 0.0;
   }
+  if (threadIdx.x == 0) { mbar_init(&xbar[0], 1); mbar_init(&xbar[1], 1); fence_mbar_init(); }
   __syncthreads();
+  cluster_sync_all();                               // every CTA's mbarriers exist before any peer signals them
   double* Tblock = (rank == 0) ? Tg + (size_t)node * npanels * 64 : nullptr;
   for (int p = 0; p < npanels; ++p) {
     const int c0 = 8 * p, pb = min(8, l - c0);
-    panel_factor_cl(S, Vtop, Tsm, tau_s, Tblock ? Tblock + (size_t)p * 64 : nullptr, sc, c0, pb, warp, lane, rank);
+    panel_factor_cl(S, Vtop, Tsm, tau_s, Tblock ? Tblock + (size_t)p * 64 : nullptr, sc, c0, pb, warp, lane, rank, xbar, xphase);
     __syncthreads();
     if (c0 + pb < l) block_reflect_cl(S, nullptr, Vtop, Tsm, sc + CLS_XW, c0, c0 + pb, l, warp, lane, rank, true, false);
     __syncthreads();
@@ -372,5 +399,5 @@ k_node_apply_cl(const ApplyTable tab, int l) {
   cluster_sync_all();
 }
 
-inline size_t cl_factor_smem(int l) { return ((size_t)l * 260 + 128 + CLS_TOTAL + (size_t)l) * sizeof(double); }
+inline size_t cl_factor_smem(int l) { return ((size_t)l * 260 + 128 + CLS_TOTAL + (size_t)l + 2) * sizeof(double); }
 inline size_t cl_apply_smem(int l) { return ((size_t)(l + 8) * 260 + 64 + (size_t)((l + 7) / 8) * 64) * sizeof(double); }

@@ -131,3 +131,44 @@ def test_sharded_randomized_pca_two_gloo_ranks(tmp_path, oracle):
     assert oracle.sigma_close(S, So)[0]
     assert abs(oracle.reconstruction_error(C, U, S, V) - oracle.reconstruction_error(C, Uo, So, Vo)) < 1e-9 * np.linalg.norm(C)
     assert np.linalg.norm(U.T @ U - np.eye(l)) < 1e-11
+
+
+def _csr_worker(rank, world, port, m, n, l, q, out_dir):
+    import scipy.sparse as sp
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle import rsvd_oracle as O
+    import sharded_model
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    M = _csr_case(m, n)
+    off, rows = W.row_split(m, world, rank)
+    U_p, S, V = sharded_model.rsvd_sharded(M[off:off + rows], W.omega(n, l), l, q, dist, torch, O)     # the shard stays a scipy CSR block
+    np.savez(Path(out_dir) / f"c{rank}.npz", U=U_p, S=S, V=V)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _csr_case(m, n):
+    import scipy.sparse as sp
+    M = sp.random(m, n, density=0.03, format="csr", random_state=np.random.default_rng(3), data_rvs=np.random.default_rng(4).standard_normal)
+    return (M + sp.eye(m, n, format="csr")).tocsr()
+
+
+def test_sharded_csr_rsvd_two_gloo_ranks(tmp_path, oracle):
+    """Row-sharded CSR (spmm.cu rsvd_csr_device with c->nranks > 1: shard-local SpMM / SpMM^T, all-reduce of the A^T Q partial
+    sums, distributed TSQR) restated with scipy.sparse + gloo on 2 CPU ranks equals the oracle on the densified matrix."""
+    import torch.multiprocessing as mp
+    m, n, l, q, world = 501, 160, 14, 2, 2
+    port = _free_port()
+    mp.spawn(_csr_worker, args=(world, port, m, n, l, q, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"c{r}.npz") for r in range(world)]
+    U = np.vstack([p["U"] for p in parts]); S = parts[0]["S"]; V = parts[0]["V"]
+    assert np.array_equal(parts[0]["S"], parts[1]["S"]) and np.array_equal(parts[0]["V"], parts[1]["V"])
+    A = np.asfortranarray(_csr_case(m, n).toarray())
+    Uo, So, Vo = oracle.rsvd(A, W.omega(n, l), l, q, oracle.JACOBI)
+    assert np.all(np.abs(S - So) <= 1e-10 * So[0])
+    assert np.linalg.norm(U.T @ U - np.eye(l)) < 1e-12
+    assert abs(oracle.reconstruction_error(A, U, S, V) - oracle.reconstruction_error(A, Uo, So, Vo)) < 1e-9 * np.linalg.norm(A)

@@ -43,6 +43,42 @@ for (m, n, l, q, gen) in [(3001, 400, 32, 2, "pod"), (20000, 1500, 100, 2, "gaus
         ok = okS and eg <= eo + 1e-8 * np.linalg.norm(A) and orthU < 1e-10 and same_S
         ok_all &= ok
         print(json.dumps({"multi_gpu": [m, n, l, q, gen], "world": world, "ok": bool(ok), "relS": relS, "err_gpu": eg, "err_oracle": eo, "orthU": orthU, "S_identical_on_all_ranks": same_S}), flush=True)
+# the ADVICE round-1 edge: shard heights straddle the wide-panel threshold 4*l (shards of 480,...,479 rows at P = 4, l = 120): every rank
+# must take the same QR branch or the collectives mismatch (pipeline.cu qr_inplace agrees on the shortest shard first)
+for l in (120,):
+    m, n, q = 4 * world * l - 1, 300, 1
+    rng = np.random.default_rng(77)
+    A = np.asfortranarray(rng.standard_normal((m, 40)) @ rng.standard_normal((40, n)) + 1e-3 * rng.standard_normal((m, n)))
+    Om = W.omega(n, l)
+    off, rows = W.row_split(m, world, rank)
+    U_p, S, V = E.rSVD(A[off:off + rows], l, SVDMethod.Jacobi, Omega=Om, q=q)
+    if rank == 0:
+        Uo, So, Vo = O.rsvd(A, Om, l, q, O.JACOBI)
+        okS, relS = O.sigma_close(S, So)
+        ok_all &= okS
+        print(json.dumps({"multi_gpu_wide_threshold": [m, n, l, q], "shard_rows": [W.row_split(m, world, r)[1] for r in range(world)], "world": world, "ok": bool(okS), "relS": relS}), flush=True)
+# row-sharded CSR (north_star: sparse .mtx inputs): every rank holds a row block of the CSR matrix, A^T Q partial sums are all-reduced
+import scipy.sparse as sp
+for (m, n, l, q, dens) in [(6001, 900, 24, 2, 0.01), (20000, 20000, 32, 1, 0.0008)]:
+    M = sp.random(m, n, density=dens, format="csr", random_state=np.random.default_rng(m), data_rvs=np.random.default_rng(m + 1).standard_normal) + sp.eye(m, n, format="csr")
+    M = M.tocsr(); M.sort_indices()
+    Om = W.omega(n, l)
+    off, rows = W.row_split(m, world, rank)
+    Mp = M[off:off + rows]
+    U_p, S, V = E.rSVD_csr(Mp.indptr.astype(np.int64), Mp.indices.astype(np.int32), Mp.data.astype(np.float64), (rows, n), l, SVDMethod.Jacobi, Omega=Om, q=q)
+    Ut = torch.from_numpy(np.ascontiguousarray(U_p)).to(dev)
+    parts = [torch.empty((W.row_split(m, world, r)[1], U_p.shape[1]), dtype=torch.float64, device=dev) for r in range(world)]
+    dist.all_gather(parts, Ut)
+    U = torch.cat(parts, 0).cpu().numpy()
+    if rank == 0:
+        A = np.asfortranarray(M.toarray())
+        Uo, So, Vo = O.rsvd(A, Om, l, q, O.JACOBI)
+        okS, relS = O.sigma_close(S, So)
+        eg, eo = O.reconstruction_error(A, U, S, V), O.reconstruction_error(A, Uo, So, Vo)
+        orthU = np.linalg.norm(U.T @ U - np.eye(U.shape[1]))
+        ok = okS and eg <= eo + 1e-8 * np.linalg.norm(A) and orthU < 1e-10
+        ok_all &= ok
+        print(json.dumps({"multi_gpu_csr": [m, n, l, q, int(M.nnz)], "world": world, "ok": bool(ok), "relS": relS, "err_gpu": eg, "err_oracle": eo, "orthU": orthU}), flush=True)
 # randomized PCA on row shards: column statistics are all-reduced, the centring corrections are applied per shard
 for (m, n, l, normalize) in [(20001, 300, 20, True), (6000, 500, 32, False)]:
     rng = np.random.default_rng(5)
