@@ -676,174 +676,6 @@ k_house_factor_la(double* __restrict__ Y, long long ldy, long long rows, int l, 
   for (int j = threadIdx.x; j < l; j += BQ_THREADS) tau_g[(size_t)blockIdx.x * l + j] = tau_s[j];
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Panel-warp factor kernel (round 2).  ncu on k_house_factor_la showed the 8-warp cooperative panel at 1.36 us per
-// reflector: every reflector paid a shared-memory exchange and a 256-thread named barrier.  Here ONE warp holds the whole
-// 256 x 8 panel in registers (lane = rows lane + 32k), so a reflector is: 8 column products per lane -> one transposed
-// warp reduction (9 shuffles) -> scalar rsqrt/rcp -> rank-1 update, with no barrier and no shared memory in the chain.
-// The products of the already finished reflectors with the current column ride in the unused slots of the same
-// reduction, which yields the compact-WY T factor without a separate Gram step.  The other 7 warps apply the previous
-// panel to the trailing columns meanwhile (look-ahead as before); all 8 warps share the look-ahead update of the next
-// panel's columns (coop_update).  256 threads per CTA so that the panel warp may use ~220 registers.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int PW_THREADS = 256;
-constexpr int PW_WARPS = PW_THREADS / 32;
-
-// Executed by one full warp.  Factors the panel [c0, c0+pb) of S (rows c0 .. BR-1), c0 a multiple of 8.
-// Writes S (storage form), Vtop (clean 8 x 8 top block), Tsm / Tglob (8 x 8 T, column-major), tau_s.
-template <int BR>
-__device__ __forceinline__ void panel_factor_w0(double* S, double* Vtop, double* Tsm, double* tau_s, double* Tglob,
-                                                int c0, int pb, int lane) {
-  static_assert(BR == 256, "eight 32-row slices per lane");
-  constexpr int LDS = BR + 4;
-  const int kd = c0 >> 5;                  // slice that holds the panel's 8 diagonal rows
-  const int l0 = c0 & 31;                  // lane of row c0 inside that slice
-  const int nb = 7 - kd;                   // slices entirely below the diagonal block
-  double ad[8];                            // slice kd:          row lane + 32 kd
-  double ab[7][8];                         // slice kd + 1 + j:  row lane + 32 (kd + 1 + j), valid for j < nb
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const double* col = S + (size_t)(c0 + c) * LDS + lane;
-    ad[c] = (c < pb) ? col[32 * kd] : 0.0;
-#pragma unroll
-    for (int j = 0; j < 7; ++j) ab[j][c] = (c < pb && j < nb) ? col[32 * (kd + 1 + j)] : 0.0;
-  }
-  double trow[8];                          // lane j < 8 keeps row j of T
-#pragma unroll
-  for (int c = 0; c < 8; ++c) trow[c] = 0.0;
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    if (r < pb) {
-      const int ld = l0 + r;               // lane that owns the diagonal row d = c0 + r
-      const double am = (lane > ld) ? ad[r] : 0.0;
-      double p[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) p[c] = am * ad[c];
-#pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        if (j < nb) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) p[c] = fma(ab[j][r], ab[j][c], p[c]);
-        }
-      }
-      double drow[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) drow[c] = __shfl_sync(0xffffffffu, ad[c], ld);
-      int colr;
-      const double sred = reduce8_transposed(p, lane, &colr);
-      double tot[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) tot[c] = __shfl_sync(0xffffffffu, sred, 4 * c);
-      const double tail = tot[r], x0 = drow[r];
-      double beta, scale, tau;
-      if (tail <= DBL_MIN) { tau = 0.0; beta = x0; scale = 0.0; }
-      else {
-        const double n2 = fma(x0, x0, tail);
-        const double inrm = rsqrt(n2);
-        const double nrm = n2 * inrm;
-        const double ax = fabs(x0);
-        beta = (x0 >= 0.0) ? -nrm : nrm;
-        tau = fma(ax, inrm, 1.0);
-        const double rc = __drcp_rn(ax + nrm);
-        scale = (x0 >= 0.0) ? rc : -rc;
-      }
-      // T(0:r, r) = -tau * T(0:r, 0:r) * (V(:, 0:r)^T v_r),  T(r, r) = tau
-      {
-        double acc = 0.0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i < r) {
-            const double z = fma(scale, tot[i], drow[i]);
-            acc = fma((i >= lane) ? trow[i] : 0.0, z, acc);
-          }
-        }
-        trow[r] = (lane < r) ? -tau * acc : (lane == r ? tau : 0.0);
-      }
-      const double vd = (lane > ld) ? ad[r] * scale : (lane == ld ? 1.0 : 0.0);
-      double vb[7];
-#pragma unroll
-      for (int j = 0; j < 7; ++j) vb[j] = ab[j][r] * scale;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (c > r) {
-          const double w = tau * fma(scale, tot[c], drow[c]);
-          ad[c] = fma(-w, vd, ad[c]);
-#pragma unroll
-          for (int j = 0; j < 7; ++j) if (j < nb) ab[j][c] = fma(-w, vb[j], ab[j][c]);
-        }
-      }
-      ad[r] = (lane > ld) ? vd : (lane == ld ? beta : ad[r]);
-#pragma unroll
-      for (int j = 0; j < 7; ++j) ab[j][r] = vb[j];
-      if (lane == 0) tau_s[c0 + r] = tau;
-    }
-  }
-  // storage form back to S (rows >= c0 only; rows above belong to R and were not touched), clean top block, T
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if (c < pb) {
-      double* col = S + (size_t)(c0 + c) * LDS + lane;
-      if (lane >= l0) col[32 * kd] = ad[c];
-#pragma unroll
-      for (int j = 0; j < 7; ++j) if (j < nb) col[32 * (kd + 1 + j)] = ab[j][c];
-    }
-    if (lane >= l0 && lane < l0 + 8) {
-      const int li = lane - l0;            // row c0 + li; diagonal of column c is row c0 + c
-      Vtop[c * 8 + li] = (c < pb) ? ((li > c) ? ad[c] : (li == c ? 1.0 : 0.0)) : 0.0;
-    }
-    if (lane < 8) { Tsm[lane + 8 * c] = trow[c]; Tglob[lane + 8 * c] = trow[c]; }
-  }
-}
-
-template <int BR>
-__global__ void __launch_bounds__(PW_THREADS, 1)
-k_house_factor_pw(double* __restrict__ Y, long long ldy, long long rows, int l, double* __restrict__ tau_g,
-                  double* __restrict__ Rstack, long long ldr, double* __restrict__ Tg) {
-  constexpr int LDS = BR + 4;
-  extern __shared__ double sm[];
-  double* S = sm;
-  double* Vtop = S + (size_t)l * LDS;              // [2][64]
-  double* Tsm = Vtop + 128;                        // [2][64]
-  double* Ws = Tsm + 128;                          // [8][64]
-  double* tau_s = Ws + 512;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long r0 = (long long)blockIdx.x * BR;
-  const int nrows = (int)min((long long)BR, rows - r0);
-  const int npanels = (l + 7) / 8;
-
-  for (int k = warp; k < l; k += PW_WARPS) {
-    const double* src = Y + (size_t)k * ldy + r0;
-    for (int i = lane; i < BR; i += 32) S[(size_t)k * LDS + i] = (i < nrows) ? src[i] : 0.0;
-  }
-  __syncthreads();
-  double* Tblock = Tg + (size_t)blockIdx.x * npanels * 64;
-  if (warp == 0) panel_factor_w0<BR>(S, Vtop, Tsm, tau_s, Tblock, 0, min(8, l), lane);
-  __syncthreads();
-  for (int p = 0; p < npanels; ++p) {
-    const int c0 = 8 * p, pb = min(8, l - c0), buf = p & 1;
-    const int n0 = c0 + pb;                        // first column of the next panel
-    if (n0 >= l) break;
-    // all 8 warps (one 32-row slab each): bring the next panel's columns up to date with panel p
-    coop_update<BR>(S, Vtop + buf * 64, Tsm + buf * 64, Ws, c0, n0, min(l, n0 + 8), warp, lane);
-    __syncthreads();
-    if (warp == 0)
-      panel_factor_w0<BR>(S, Vtop + (buf ^ 1) * 64, Tsm + (buf ^ 1) * 64, tau_s, Tblock + (size_t)(p + 1) * 64, n0, min(8, l - n0), lane);
-    else if (n0 + 8 < l)
-      block_reflect_s<BR>(S, Vtop + buf * 64, Tsm + buf * 64, c0, n0 + 8, l, warp - 1, PW_WARPS - 1, lane);
-    __syncthreads();
-  }
-  double* Rb = Rstack + (size_t)blockIdx.x * l;
-  for (int k = warp; k < l; k += PW_WARPS) {
-    double* dst = Y + (size_t)k * ldy + r0;
-    for (int i = lane; i < BR; i += 32) {
-      const double val = S[(size_t)k * LDS + i];
-      if (i < nrows) dst[i] = val;
-      if (i < l) Rb[(size_t)k * ldr + i] = (i <= k) ? val : 0.0;
-    }
-  }
-  for (int j = threadIdx.x; j < l; j += PW_THREADS) tau_g[(size_t)blockIdx.x * l + j] = tau_s[j];
-}
-
 // Up to 16 tree levels can be processed by one launch (their blocks are independent when every level starts from the
 // identity): the block looks its level up in this table.
 struct ApplyLevel { const double* V; long long ldv; long long rows; const double* Tg; const double* Ctop; long long ldc; double* Q; long long ldq; int first_block; };
@@ -1055,7 +887,6 @@ int pick_br(int l) {
   return 0;
 }
 
-bool old_leaf() { static int m = -1; if (m < 0) m = getenv("RSVDB_TSQR_OLD_LEAF") ? 1 : 0; return m == 1; }   // A/B switch for profiling
 int cl_max_nodes() { static int m = -1; if (m < 0) { const char* e = getenv("RSVDB_TSQR_CL_MAX"); m = e ? atoi(e) : 99; } return m; }
 
 size_t blk_smem_bytes(int l) { return ((size_t)(l + 8) * (256 + 4) + 64 + 720 + (size_t)l) * sizeof(double); }
@@ -1066,8 +897,6 @@ cudaError_t set_attr_blk_once() {
   cudaError_t e = cudaFuncSetAttribute(k_house_apply_blk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_house_factor_la<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_house_factor_pw<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_node_factor_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
@@ -1146,8 +975,6 @@ cudaError_t Tsqr::factor(cudaStream_t st, double* Y, long long ldy, int* launche
       e = set_attr_blk_once(); if (e != cudaSuccess) return e;
       if (L.cl)
         k_node_factor_cl<<<L.nb * CL, BQ_THREADS, cl_factor_smem(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
-      else if (!old_leaf())
-        k_house_factor_pw<256><<<L.nb, PW_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
       else
         k_house_factor_la<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
     } else
