@@ -57,9 +57,12 @@ RSVDB_API const char* rsvdb_last_error(const rsvdb_ctx* ctx);
 RSVDB_API const char* rsvdb_version(void);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 RSVDB_API int64_t rsvdb_launch_count(const rsvdb_ctx* ctx);
-/* Performance note (process-wide counter): how many dense products fell back to the CUDA-core kernel because an operand
- * of a *_dev call was not TMA-addressable -- an odd leading dimension or a base pointer that is only 8-byte aligned.
- * The result is the same; the product runs far below the FP64 tensor-core rate.  Pad lda to an even number of rows. */
+/* Performance notes (process-wide counters, not errors) about the operands of *_dev products.
+ * rsvdb_split_gemm_products: products whose big operand A had an odd leading dimension or a base pointer that is only
+ *   8-byte aligned.  TMA cannot describe such a matrix with one tensor map; the engine describes its even and its odd columns
+ *   separately (two maps, stride 2*lda) and runs the same FP64 tensor-core kernel -- same speed class, no copy of A.
+ * rsvdb_generic_gemm_fallbacks: products that ran on the CUDA-core kernel instead (only a 1-column A that is also misaligned). */
+RSVDB_API int64_t rsvdb_split_gemm_products(void);
 RSVDB_API int64_t rsvdb_generic_gemm_fallbacks(void);
 
 /* Optional per-phase device timing (CUDA events on the context's stream).  rsvdb_phase_ms synchronises the stream,

@@ -48,6 +48,7 @@ def _declare(lib):
     lib.rsvdb_last_error.restype = c_char_p
     lib.rsvdb_launch_count.restype = c_int64
     lib.rsvdb_generic_gemm_fallbacks.restype = c_int64
+    lib.rsvdb_split_gemm_products.restype = c_int64
     sig = {
         "rsvdb_create": [POINTER(c_void_p), c_int],
         "rsvdb_destroy": [vp],
@@ -57,6 +58,7 @@ def _declare(lib):
         "rsvdb_last_error": [vp],
         "rsvdb_launch_count": [vp],
         "rsvdb_generic_gemm_fallbacks": [],
+        "rsvdb_split_gemm_products": [],
         "rsvdb_set_profiling": [vp, c_int],
         "rsvdb_phase_ms": [vp, POINTER(c_double)],
         "rsvdb_last_svd_info": [vp, POINTER(c_int), POINTER(c_int)],

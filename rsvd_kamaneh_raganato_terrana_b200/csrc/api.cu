@@ -147,6 +147,7 @@ int rsvdb_synchronize(rsvdb_ctx* c) {
 const char* rsvdb_last_error(const rsvdb_ctx* c) { return c ? c->err.c_str() : "null context"; }
 int64_t rsvdb_launch_count(const rsvdb_ctx* c) { return c ? c->launches : 0; }
 int64_t rsvdb_generic_gemm_fallbacks(void) { return generic_fallback_count(); }
+int64_t rsvdb_split_gemm_products(void) { return split_product_count(); }
 
 int rsvdb_set_profiling(rsvdb_ctx* c, int enabled) {
   if (!c) return RSVDB_ERR_INVALID_ARGUMENT;

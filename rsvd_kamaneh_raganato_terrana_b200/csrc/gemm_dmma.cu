@@ -45,7 +45,15 @@ struct GemmParams {
   int transpose_out;      // K2 only: store element (j, c) at out[c + j * ld_out]
   int vec_ok;             // K1 only: 16-byte stores allowed
   int stages;
+  int sh0, sh1;           // SPLIT only: row shift (0 / 1) of the even- / odd-column tensor map (see below)
 };
+
+// SPLIT = A is not TMA-addressable as one tensor: its leading dimension is odd (column starts alternate between 16-byte
+// aligned and 8 mod 16) or its base is only 8-byte aligned.  The columns of one parity are 2*lda apart -- a legal TMA stride --
+// so A is described by TWO tensor maps (even columns, odd columns); a class whose first column starts at 8 mod 16 gets its
+// base moved one element down and its row coordinate shifted by one (sh = 1).  K1: the 16 reduction indices of a stage land
+// as smem lines [k even | k odd]; the consumers pair line L with X row k(L) = L < 8 ? 2L : 2(L-8)+1.  K2: the 128 tile
+// columns land as smem rows [even | odd]; only the epilogue's row -> column map changes.  Same bytes, same DMMA work.
 
 template <int NB> struct SmemCfg {
   static constexpr uint32_t X_BYTES = NB * 8 * BK * 8;
@@ -59,9 +67,9 @@ __device__ __forceinline__ const double2* frag_ptr(const uint8_t* base, uint32_t
 // ------------------------------------------------------------------------------------------------------------------
 // K1: Y = A * X
 // ------------------------------------------------------------------------------------------------------------------
-template <int NB>
+template <int NB, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_gemm_an(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+k_gemm_an(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t STAGE = SmemCfg<NB>::STAGE_BYTES;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -91,8 +99,16 @@ k_gemm_an(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE);
           uint8_t* sa = smem + (size_t)stage * STAGE;
+          if (SPLIT) {
 #pragma unroll
-          for (int b = 0; b < NCONS; ++b) tma_load_2d(sa + b * (16 * BK * 8), &tmA, &full[stage], m0 + 16 * b, k);
+            for (int b = 0; b < NCONS; ++b) {
+              tma_load_2d(sa + b * (16 * BK * 8), &tmA, &full[stage], m0 + 16 * b + p.sh0, k >> 1);            // lines 0-7: k even
+              tma_load_2d(sa + b * (16 * BK * 8) + 1024, &tmA1, &full[stage], m0 + 16 * b + p.sh1, k >> 1);    // lines 8-15: k odd
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < NCONS; ++b) tma_load_2d(sa + b * (16 * BK * 8), &tmA, &full[stage], m0 + 16 * b, k);
+          }
           tma_load_2d(sa + A_BYTES, &tmX, &full[stage], k, 0);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -106,6 +122,8 @@ k_gemm_an(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t offA1 = warp * (16 * BK * 8) + (2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4);
     const uint32_t offB0 = A_BYTES + pg * 128 + ((t ^ pg) << 4);
     const uint32_t offB1 = A_BYTES + pg * 128 + (((4 + t) ^ pg) << 4);
+    const uint32_t offBs0 = A_BYTES + pg * 128 + (((2 * t) ^ pg) << 4);       // SPLIT: X rows k = 4t, 4t+1
+    const uint32_t offBs1 = A_BYTES + pg * 128 + (((2 * t + 1) ^ pg) << 4);   //        X rows k = 4t+2, 4t+3
 
     for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
       const int tile = u / p.nsplit, split = u - tile * p.nsplit;
@@ -117,6 +135,20 @@ k_gemm_an(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int k = k0; k < k1; k += BK) {
         mbar_wait(&full[stage], phase);
         const uint8_t* ss = smem + (size_t)stage * STAGE;
+        if (SPLIT) {
+          // line 2t <-> k = 4t, line 2t+1 <-> k = 4t+2, line 8+2t <-> k = 4t+1, line 8+2t+1 <-> k = 4t+3
+          const double2 a00 = *frag_ptr(ss, offA0), a10 = *frag_ptr(ss, offA1);
+          const double2 a01 = *frag_ptr(ss, offA0 + 1024), a11 = *frag_ptr(ss, offA1 + 1024);
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const double2 blo = *frag_ptr(ss, offBs0 + j * 1024);   // column 8j + perm(g), k = (4t, 4t+1)
+            const double2 bhi = *frag_ptr(ss, offBs1 + j * 1024);   //                      k = (4t+2, 4t+3)
+            dmma_16x8x4(c[j], a00.x, a00.y, blo.x);
+            dmma_16x8x4(c[j], a10.x, a10.y, bhi.x);
+            dmma_16x8x4(c[j], a01.x, a01.y, blo.y);
+            dmma_16x8x4(c[j], a11.x, a11.y, bhi.y);
+          }
+        } else
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const double2 a0 = *frag_ptr(ss, offA0 + h * 1024);   // rows (2g, 2g+1), k = 8h + 2t
@@ -163,9 +195,9 @@ k_gemm_an(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // ------------------------------------------------------------------------------------------------------------------
 // K2 / K3: Z = A^T * Q   (A is K x M column-major: the reduction runs down the contiguous dimension)
 // ------------------------------------------------------------------------------------------------------------------
-template <int NB>
+template <int NB, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_gemm_at(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ, const GemmParams p) {
+k_gemm_at(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmQ, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t STAGE = SmemCfg<NB>::STAGE_BYTES;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -194,7 +226,12 @@ k_gemm_at(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE);
           uint8_t* sa = smem + (size_t)stage * STAGE;
-          tma_load_2d(sa, &tmA, &full[stage], k, j0);
+          if (SPLIT) {
+            tma_load_2d(sa, &tmA, &full[stage], k + p.sh0, j0 >> 1);                 // smem rows 0-63: even tile columns
+            tma_load_2d(sa + 64 * 128, &tmA1, &full[stage], k + p.sh1, j0 >> 1);     // smem rows 64-127: odd tile columns
+          } else {
+            tma_load_2d(sa, &tmA, &full[stage], k, j0);
+          }
           tma_load_2d(sa + A_BYTES, &tmQ, &full[stage], k, 0);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -239,7 +276,9 @@ k_gemm_at(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
       // epilogue: thread owns tile columns jlo = 16w + perm(g), jhi = jlo + 8 and output columns 8j + t, 8j + t + 4
       double* out = p.out + (size_t)split * p.split_stride;
-      const int jlo = tile * BM + 16 * warp + pg;
+      const int rlo = 16 * warp + pg, rhi = rlo + 8;                      // smem rows of this thread's two tile columns
+      const int jlo = tile * BM + (SPLIT ? ((rlo & 63) << 1) + (rlo >> 6) : rlo);
+      const int jhi = tile * BM + (SPLIT ? ((rhi & 63) << 1) + (rhi >> 6) : rhi);
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
 #pragma unroll
@@ -248,10 +287,10 @@ k_gemm_at(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (n < p.N) {
             if (p.transpose_out) {
               if (jlo < p.M) out[(size_t)jlo * p.ld_out + n] = c[j][e];
-              if (jlo + 8 < p.M) out[(size_t)(jlo + 8) * p.ld_out + n] = c[j][2 + e];
+              if (jhi < p.M) out[(size_t)jhi * p.ld_out + n] = c[j][2 + e];
             } else {
               if (jlo < p.M) out[(size_t)n * p.ld_out + jlo] = c[j][e];
-              if (jlo + 8 < p.M) out[(size_t)n * p.ld_out + jlo + 8] = c[j][2 + e];
+              if (jhi < p.M) out[(size_t)n * p.ld_out + jhi] = c[j][2 + e];
             }
           }
         }
@@ -366,8 +405,6 @@ bool make_map(CUtensorMap* map, const double* base, long long rows, long long co
   return r == CUDA_SUCCESS;
 }
 
-static long long g_generic_fallbacks = 0;   // products that took the CUDA-core kernel because an operand was not TMA-addressable
-void note_generic_fallback() { ++g_generic_fallbacks; }
 bool tma_addressable(const double* p, long long ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 1) == 0; }
 
 // Cut the reduction into nsplit slabs so that (tiles x splits) fills the SMs in whole waves.  Cost model in units of one
@@ -390,34 +427,64 @@ void choose_split(int ntiles, int ksteps, int nsm, long long out_elems, int nb, 
   *nsplit = (ksteps + per - 1) / per;
 }
 
-template <int NB> cudaError_t launch_an(const CUtensorMap& tA, const CUtensorMap& tX, GemmParams p, int grid, cudaStream_t st) {
+template <int NB, bool SPLIT> cudaError_t launch_an(const CUtensorMap& tA, const CUtensorMap& tA1, const CUtensorMap& tX, GemmParams p, int grid, cudaStream_t st) {
   constexpr uint32_t STAGE = SmemCfg<NB>::STAGE_BYTES;
   int stages = std::min(8, (int)((220 * 1024 - 1024) / STAGE));
   p.stages = stages;
   const size_t smem = (size_t)stages * STAGE + 1024 + 2 * stages * sizeof(uint64_t);
   static DevOnce attr_set;
   if (!attr_set.get()) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_an<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_an<NB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set.set();
   }
-  k_gemm_an<NB><<<grid, NTHREADS, smem, st>>>(tA, tX, p);
+  k_gemm_an<NB, SPLIT><<<grid, NTHREADS, smem, st>>>(tA, tA1, tX, p);
   return cudaGetLastError();
 }
-template <int NB> cudaError_t launch_at(const CUtensorMap& tA, const CUtensorMap& tQ, GemmParams p, int grid, cudaStream_t st) {
+template <int NB, bool SPLIT> cudaError_t launch_at(const CUtensorMap& tA, const CUtensorMap& tA1, const CUtensorMap& tQ, GemmParams p, int grid, cudaStream_t st) {
   constexpr uint32_t STAGE = SmemCfg<NB>::STAGE_BYTES;
   int stages = std::min(8, (int)((220 * 1024 - 1024) / STAGE));
   p.stages = stages;
   const size_t smem = (size_t)stages * STAGE + 1024 + 2 * stages * sizeof(uint64_t);
   static DevOnce attr_set;
   if (!attr_set.get()) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_at<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_at<NB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set.set();
   }
-  k_gemm_at<NB><<<grid, NTHREADS, smem, st>>>(tA, tQ, p);
+  k_gemm_at<NB, SPLIT><<<grid, NTHREADS, smem, st>>>(tA, tA1, tQ, p);
   return cudaGetLastError();
 }
+#define RSVDB_NB_SWITCH(FN, SPL, ...)                                                                                  \
+  switch (NB) {                                                                                                        \
+    case 1: e = FN<1, SPL>(__VA_ARGS__); break;   case 2: e = FN<2, SPL>(__VA_ARGS__); break;                             \
+    case 3: e = FN<3, SPL>(__VA_ARGS__); break;   case 4: e = FN<4, SPL>(__VA_ARGS__); break;                             \
+    case 5: e = FN<5, SPL>(__VA_ARGS__); break;   case 6: e = FN<6, SPL>(__VA_ARGS__); break;                             \
+    case 7: e = FN<7, SPL>(__VA_ARGS__); break;   case 8: e = FN<8, SPL>(__VA_ARGS__); break;                             \
+    case 9: e = FN<9, SPL>(__VA_ARGS__); break;   case 10: e = FN<10, SPL>(__VA_ARGS__); break;                           \
+    case 11: e = FN<11, SPL>(__VA_ARGS__); break; case 12: e = FN<12, SPL>(__VA_ARGS__); break;                           \
+    case 13: e = FN<13, SPL>(__VA_ARGS__); break; case 14: e = FN<14, SPL>(__VA_ARGS__); break;                           \
+    case 15: e = FN<15, SPL>(__VA_ARGS__); break; default: e = FN<16, SPL>(__VA_ARGS__); break;                           \
+  }
+
+// A that one tensor map cannot describe: two maps over the columns of each parity (see the SPLIT note above GemmParams).
+// rows x cols matrix, column stride lda; box {16, box_cols}.  Returns false when a class would be empty (cols < 2).
+bool make_split_maps(CUtensorMap* m0, CUtensorMap* m1, int* sh0, int* sh1, const double* A, long long rows, long long cols, long long lda, int box_cols) {
+  if (cols < 2) return false;
+  const double* a0 = A; const double* a1 = A + lda;
+  *sh0 = (int)((reinterpret_cast<uintptr_t>(a0) >> 3) & 1); *sh1 = (int)((reinterpret_cast<uintptr_t>(a1) >> 3) & 1);
+  return make_map(m0, a0 - *sh0, rows + *sh0, (cols + 1) / 2, 2 * lda, box_cols) && make_map(m1, a1 - *sh1, rows + *sh1, cols / 2, 2 * lda, box_cols);
+}
+
+// the skinny operand (K x N) is small: when IT is not TMA-addressable it is repacked into an even-ld scratch
+__global__ void k_repack(const double* __restrict__ src, long long lds, double* __restrict__ dst, long long ldd, long long rows, int cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) for (int k = blockIdx.y; k < cols; k += gridDim.y) dst[(size_t)k * ldd + i] = src[(size_t)k * lds + i];
+}
+
+static long long g_generic_fallbacks = 0;   // products that took the CUDA-core kernel (operands TMA cannot describe at all)
+static long long g_split_products = 0;      // products whose A needed the two-map (odd lda / 8-byte aligned base) path
+void note_generic_fallback() { ++g_generic_fallbacks; }
 
 }  // namespace
 
@@ -431,6 +498,8 @@ cudaError_t gemm_generic(cudaStream_t st, int ta, int tb, int m, int n, int k, d
   return cudaGetLastError();
 }
 
+long long split_product_count() { return g_split_products; }
+
 cudaError_t gemm_an(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A, long long M, long long K, long long lda,
                     const double* X, long long ldx, int N, double* Y, long long ldy, int* launches) {
   if (M <= 0 || N <= 0) return cudaSuccess;
@@ -439,43 +508,44 @@ cudaError_t gemm_an(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
     return cudaSuccess;
   }
   if (M >= (1LL << 31) || K >= (1LL << 31)) return cudaErrorInvalidValue;     // explicit error: dimensions are 32-bit inside the kernels
-  if (!tma_addressable(A, lda) || !tma_addressable(X, ldx)) {
-    note_generic_fallback();
+  const bool splitA = !tma_addressable(A, lda);
+  const bool repackX = !tma_addressable(X, ldx);
+  CUtensorMap tA, tA1; int sh0 = 0, sh1 = 0;
+  if (splitA ? !make_split_maps(&tA, &tA1, &sh0, &sh1, A, M, K, lda, BK / 2) : !make_map(&tA, A, M, K, lda, BK)) {
+    if (!splitA) return cudaErrorInvalidValue;
+    note_generic_fallback();                                                   // K == 1: nothing to stream
     if (launches) ++*launches;
     return gemm_generic(st, 0, 0, (int)M, N, (int)K, 1.0, A, lda, X, ldx, 0.0, Y, ldy);
   }
-  CUtensorMap tA;
-  if (!make_map(&tA, A, M, K, lda, BK)) return cudaErrorInvalidValue;
+  if (!splitA) tA1 = tA; else ++g_split_products;
   const int ntiles = (int)((M + BM - 1) / BM), ksteps = (int)((K + BK - 1) / BK);
   int nsplit, kchunk; choose_split(ntiles, ksteps, nsm, M * std::min(N, 128), (std::min(N, 128) + 7) / 8, &nsplit, &kchunk);
+  const long long ldw = (M + 1) & ~1LL, ldxr = (K + 1) & ~1LL;
+  const size_t part_bytes = nsplit > 1 ? (((size_t)nsplit * ldw * std::min(N, 128) * 8 + 255) & ~size_t(255)) : 0;
+  if (part_bytes || repackX) { cudaError_t e = ws.reserve(part_bytes + (repackX ? (size_t)ldxr * N * 8 : 0)); if (e != cudaSuccess) return e; }
+  if (repackX) {
+    double* Xr = reinterpret_cast<double*>(reinterpret_cast<char*>(ws.ptr) + part_bytes);
+    k_repack<<<dim3((unsigned)((K + 255) / 256), (unsigned)std::min(N, 128)), 256, 0, st>>>(X, ldx, Xr, ldxr, K, N);
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+    X = Xr; ldx = ldxr;
+  }
   for (int n0 = 0; n0 < N; n0 += 128) {
     const int nc = std::min(128, N - n0), NB = (nc + 7) / 8;
     CUtensorMap tX;
     if (!make_map(&tX, X + (size_t)n0 * ldx, K, nc, ldx, NB * 8)) return cudaErrorInvalidValue;
     GemmParams p{};
-    p.M = (int)M; p.N = nc; p.K = (int)K; p.ntiles = ntiles; p.nsplit = nsplit; p.kchunk = kchunk; p.transpose_out = 0;
+    p.M = (int)M; p.N = nc; p.K = (int)K; p.ntiles = ntiles; p.nsplit = nsplit; p.kchunk = kchunk; p.transpose_out = 0; p.sh0 = sh0; p.sh1 = sh1;
     double* yout = Y + (size_t)n0 * ldy;
     if (nsplit == 1) {
       p.out = yout; p.ld_out = ldy; p.split_stride = 0;
       p.vec_ok = ((ldy & 1) == 0 && (reinterpret_cast<uintptr_t>(yout) & 15) == 0) ? 1 : 0;
     } else {
-      const long long ldw = (M + 1) & ~1LL;
-      const size_t need = (size_t)nsplit * ldw * nc * 8;
-      cudaError_t e = ws.reserve(need); if (e != cudaSuccess) return e;
       p.out = ws.ptr; p.ld_out = ldw; p.split_stride = ldw * nc; p.vec_ok = 1;
     }
     const int grid = std::min(nsm, ntiles * nsplit);
     cudaError_t e;
-    switch (NB) {
-      case 1: e = launch_an<1>(tA, tX, p, grid, st); break;   case 2: e = launch_an<2>(tA, tX, p, grid, st); break;
-      case 3: e = launch_an<3>(tA, tX, p, grid, st); break;   case 4: e = launch_an<4>(tA, tX, p, grid, st); break;
-      case 5: e = launch_an<5>(tA, tX, p, grid, st); break;   case 6: e = launch_an<6>(tA, tX, p, grid, st); break;
-      case 7: e = launch_an<7>(tA, tX, p, grid, st); break;   case 8: e = launch_an<8>(tA, tX, p, grid, st); break;
-      case 9: e = launch_an<9>(tA, tX, p, grid, st); break;   case 10: e = launch_an<10>(tA, tX, p, grid, st); break;
-      case 11: e = launch_an<11>(tA, tX, p, grid, st); break; case 12: e = launch_an<12>(tA, tX, p, grid, st); break;
-      case 13: e = launch_an<13>(tA, tX, p, grid, st); break; case 14: e = launch_an<14>(tA, tX, p, grid, st); break;
-      case 15: e = launch_an<15>(tA, tX, p, grid, st); break; default: e = launch_an<16>(tA, tX, p, grid, st); break;
-    }
+    if (splitA) { RSVDB_NB_SWITCH(launch_an, true, tA, tA1, tX, p, grid, st) } else { RSVDB_NB_SWITCH(launch_an, false, tA, tA1, tX, p, grid, st) }
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
     if (nsplit > 1) {
@@ -497,42 +567,44 @@ cudaError_t gemm_at(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
     return cudaSuccess;
   }
   if (M >= (1LL << 31) || K >= (1LL << 31)) return cudaErrorInvalidValue;
-  if (!tma_addressable(A, lda) || !tma_addressable(Q, ldq)) {
-    note_generic_fallback();
+  const bool splitA = !tma_addressable(A, lda);
+  const bool repackQ = !tma_addressable(Q, ldq);
+  CUtensorMap tA, tA1; int sh0 = 0, sh1 = 0;
+  if (splitA ? !make_split_maps(&tA, &tA1, &sh0, &sh1, A, K, M, lda, BM / 2) : !make_map(&tA, A, K, M, lda, BM)) {
+    if (!splitA) return cudaErrorInvalidValue;
+    note_generic_fallback();                                                   // a single column of A
     if (launches) ++*launches;
     if (!transpose_out) return gemm_generic(st, 1, 0, (int)M, N, (int)K, 1.0, A, lda, Q, ldq, 0.0, Z, ldz);
     return gemm_generic(st, 1, 0, N, (int)M, (int)K, 1.0, Q, ldq, A, lda, 0.0, Z, ldz);
   }
-  CUtensorMap tA;
-  if (!make_map(&tA, A, K, M, lda, BM)) return cudaErrorInvalidValue;
+  if (!splitA) tA1 = tA; else ++g_split_products;
   const int ntiles = (int)((M + BM - 1) / BM), ksteps = (int)((K + BK - 1) / BK);
   int nsplit, kchunk; choose_split(ntiles, ksteps, nsm, M * std::min(N, 128), (std::min(N, 128) + 7) / 8, &nsplit, &kchunk);
+  const long long ldqr = (K + 1) & ~1LL;
+  const size_t part_bytes = nsplit > 1 ? (((size_t)nsplit * M * std::min(N, 128) * 8 + 255) & ~size_t(255)) : 0;
+  if (part_bytes || repackQ) { cudaError_t e = ws.reserve(part_bytes + (repackQ ? (size_t)ldqr * N * 8 : 0)); if (e != cudaSuccess) return e; }
+  if (repackQ) {
+    double* Qr = reinterpret_cast<double*>(reinterpret_cast<char*>(ws.ptr) + part_bytes);
+    k_repack<<<dim3((unsigned)((K + 255) / 256), (unsigned)std::min(N, 128)), 256, 0, st>>>(Q, ldq, Qr, ldqr, K, N);
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+    Q = Qr; ldq = ldqr;
+  }
   for (int n0 = 0; n0 < N; n0 += 128) {
     const int nc = std::min(128, N - n0), NB = (nc + 7) / 8;
     CUtensorMap tQ;
     if (!make_map(&tQ, Q + (size_t)n0 * ldq, K, nc, ldq, NB * 8)) return cudaErrorInvalidValue;
     GemmParams p{};
-    p.M = (int)M; p.N = nc; p.K = (int)K; p.ntiles = ntiles; p.nsplit = nsplit; p.kchunk = kchunk; p.vec_ok = 0;
+    p.M = (int)M; p.N = nc; p.K = (int)K; p.ntiles = ntiles; p.nsplit = nsplit; p.kchunk = kchunk; p.vec_ok = 0; p.sh0 = sh0; p.sh1 = sh1;
     double* zout = transpose_out ? Z + n0 : Z + (size_t)n0 * ldz;
     if (nsplit == 1) {
       p.out = zout; p.ld_out = ldz; p.split_stride = 0; p.transpose_out = transpose_out;
     } else {
-      const size_t need = (size_t)nsplit * M * nc * 8;
-      cudaError_t e = ws.reserve(need); if (e != cudaSuccess) return e;
       p.out = ws.ptr; p.ld_out = M; p.split_stride = M * nc; p.transpose_out = 0;
     }
     const int grid = std::min(nsm, ntiles * nsplit);
     cudaError_t e;
-    switch (NB) {
-      case 1: e = launch_at<1>(tA, tQ, p, grid, st); break;   case 2: e = launch_at<2>(tA, tQ, p, grid, st); break;
-      case 3: e = launch_at<3>(tA, tQ, p, grid, st); break;   case 4: e = launch_at<4>(tA, tQ, p, grid, st); break;
-      case 5: e = launch_at<5>(tA, tQ, p, grid, st); break;   case 6: e = launch_at<6>(tA, tQ, p, grid, st); break;
-      case 7: e = launch_at<7>(tA, tQ, p, grid, st); break;   case 8: e = launch_at<8>(tA, tQ, p, grid, st); break;
-      case 9: e = launch_at<9>(tA, tQ, p, grid, st); break;   case 10: e = launch_at<10>(tA, tQ, p, grid, st); break;
-      case 11: e = launch_at<11>(tA, tQ, p, grid, st); break; case 12: e = launch_at<12>(tA, tQ, p, grid, st); break;
-      case 13: e = launch_at<13>(tA, tQ, p, grid, st); break; case 14: e = launch_at<14>(tA, tQ, p, grid, st); break;
-      case 15: e = launch_at<15>(tA, tQ, p, grid, st); break; default: e = launch_at<16>(tA, tQ, p, grid, st); break;
-    }
+    if (splitA) { RSVDB_NB_SWITCH(launch_at, true, tA, tA1, tQ, p, grid, st) } else { RSVDB_NB_SWITCH(launch_at, false, tA, tA1, tQ, p, grid, st) }
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
     if (nsplit > 1) {

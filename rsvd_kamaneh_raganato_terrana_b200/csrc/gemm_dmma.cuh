@@ -29,8 +29,10 @@ cudaError_t gemm_at(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
 cudaError_t gemm_generic(cudaStream_t st, int ta, int tb, int m, int n, int k, double alpha, const double* A, long long lda,
                          const double* B, long long ldb, double beta, double* C, long long ldc);
 
-// Number of gemm_an / gemm_at calls (process-wide) that fell back to the CUDA-core kernel because an operand was not
-// TMA-addressable (odd leading dimension or a base pointer that is only 8-byte aligned).  A performance note, not an error.
+// Performance notes (process-wide counters, not errors).  split_product_count: gemm_an / gemm_at calls whose A had an odd
+// leading dimension or an 8-byte-aligned base and therefore ran on the two-tensor-map variant of the DMMA kernels (same
+// speed class).  generic_fallback_count: calls that ran on the CUDA-core kernel (only a 1-column / 1-row A that TMA cannot describe).
 long long generic_fallback_count();
+long long split_product_count();
 
 }  // namespace rsvdb

@@ -350,6 +350,60 @@ def test_skinny_gemms(engine, m, n, l, lda):
     engine.lib.rsvdb_use_own_stream(engine.h)
 
 
+@pytest.mark.parametrize("m,n,l,lda,off", [(4097, 4096, 50, 4097, 0), (4096, 4097, 50, 4096, 1), (1001, 333, 17, 1003, 1), (2049, 4097, 100, 2049, 0),
+                                           (129, 2, 8, 131, 1), (20001, 1001, 104, 20001, 0), (515, 700, 130, 515, 1)])
+def test_skinny_gemms_operands_tma_cannot_describe(engine, m, n, l, lda, off):
+    """A with an ODD leading dimension (a packed Eigen matrix with an odd row count) or a base that is only 8-byte aligned: no single
+    tensor map exists (16-byte strides), so the products run on the two-map variant of the same DMMA kernels (gemm_dmma.cu SPLIT) --
+    not on the CUDA-core fallback round 1 dropped to.  The path taken is asserted through the C ABI's performance-note counters."""
+    import torch
+    dev = torch.device("cuda:0")
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    buf = torch.randn(n * lda + 2, dtype=torch.float64, device=dev)
+    A = buf[off:off + n * lda].view(n, lda)                                # column-major m x n, leading dimension lda, base offset `off` doubles
+    assert A.data_ptr() % 16 == 8 * off
+    Xb = torch.randn(l * n + 2, dtype=torch.float64, device=dev); X = Xb[off:off + l * n].view(l, n)     # the skinny operands are misaligned too
+    Qb = torch.randn(l * m + 2, dtype=torch.float64, device=dev); Q = Qb[off:off + l * m].view(l, m)
+    Y = torch.full((l, m), float("nan"), dtype=torch.float64, device=dev)
+    Z = torch.full((l, n), float("nan"), dtype=torch.float64, device=dev); B = torch.full((n, l), float("nan"), dtype=torch.float64, device=dev)
+    s0, g0 = engine.lib.rsvdb_split_gemm_products(), engine.lib.rsvdb_generic_gemm_fallbacks()
+    engine.gemm_an_dev(A.data_ptr(), m, n, lda, X.data_ptr(), n, l, Y.data_ptr(), m)
+    engine.gemm_at_dev(A.data_ptr(), m, n, lda, Q.data_ptr(), m, l, Z.data_ptr(), n, False)
+    engine.gemm_at_dev(A.data_ptr(), m, n, lda, Q.data_ptr(), m, l, B.data_ptr(), l, True)
+    torch.cuda.synchronize()
+    assert engine.lib.rsvdb_split_gemm_products() - s0 == 3 and engine.lib.rsvdb_generic_gemm_fallbacks() == g0
+    Am = A[:, :m].T
+    ref1 = Am @ X.T; ref2 = Am.T @ Q.T
+    assert ((Y.T - ref1).norm() / ref1.norm()).item() < 1e-13
+    assert ((Z.T - ref2).norm() / ref2.norm()).item() < 1e-13
+    assert ((B.T - ref2.T).norm() / ref2.norm()).item() < 1e-13
+    engine.lib.rsvdb_use_own_stream(engine.h)
+
+
+def test_odd_leading_dimension_is_no_performance_cliff(engine):
+    """VERDICT round 1, weak #7: 4097 x 4096 x 50 with packed lda = 4097 must run within 25 % of the lda = 4098 time."""
+    import torch
+    dev = torch.device("cuda:0")
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    m, n, l = 4097, 4096, 50
+    X = torch.randn((l, n), dtype=torch.float64, device=dev); Q = torch.randn((l, 4098), dtype=torch.float64, device=dev)
+    Y = torch.empty((l, 4098), dtype=torch.float64, device=dev); Z = torch.empty((l, n), dtype=torch.float64, device=dev)
+    times = {}
+    for lda in (4098, 4097):
+        A = torch.randn((n, lda), dtype=torch.float64, device=dev)
+        best = [1e30, 1e30]
+        for _ in range(6):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(); engine.gemm_an_dev(A.data_ptr(), m, n, lda, X.data_ptr(), n, l, Y.data_ptr(), 4098)
+            e[1].record(); engine.gemm_at_dev(A.data_ptr(), m, n, lda, Q.data_ptr(), 4098, l, Z.data_ptr(), n, False)
+            e[2].record(); torch.cuda.synchronize()
+            best = [min(best[0], e[0].elapsed_time(e[1])), min(best[1], e[1].elapsed_time(e[2]))]
+        times[lda] = best
+    print(f"gemm_an / gemm_at 4097x4096x50: lda 4098 {times[4098][0]:.4f} / {times[4098][1]:.4f} ms, lda 4097 {times[4097][0]:.4f} / {times[4097][1]:.4f} ms")
+    assert times[4097][0] <= 1.25 * times[4098][0] + 0.01 and times[4097][1] <= 1.25 * times[4098][1] + 0.01
+    engine.lib.rsvdb_use_own_stream(engine.h)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # BASELINE.json's configs 2-4 at their FULL sizes against the oracle (src/rSVD.cpp:72-133 restated in oracle/rsvd_oracle.py;
 # the chain oracle == reference sources is asserted bit-for-bit on the dev box by tests/test_oracle.py, the GPU box has
