@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace rsvdb {
 
@@ -45,16 +46,19 @@ struct GemmParams {
   int transpose_out;      // K2 only: store element (j, c) at out[c + j * ld_out]
   int vec_ok;             // K1 only: 16-byte stores allowed
   int stages;
-  int sh0, sh1;           // SPLIT only: row shift (0 / 1) of the even- / odd-column tensor map (see below)
+  int sh0, sh1;           // SPLIT only: 1 = the even- / odd-column class starts at 8 mod 16 and is copied with cp.async
+  const double* Araw;     // SPLIT only: A and its leading dimension for the cp.async classes
+  long long lda;
 };
 
 // SPLIT = A is not TMA-addressable as one tensor: its leading dimension is odd (column starts alternate between 16-byte
 // aligned and 8 mod 16) or its base is only 8-byte aligned.  The columns of one parity are 2*lda apart -- a legal TMA stride --
-// so A is described by TWO tensor maps (even columns, odd columns); a class whose first column starts at 8 mod 16 gets its
-// base moved one element down and its row coordinate shifted by one (sh = 1).  K1: the 16 reduction indices of a stage land
-// as smem lines [k even | k odd]; the consumers pair line L with X row k(L) = L < 8 ? 2L : 2(L-8)+1.  K2: the 128 tile
-// columns land as smem rows [even | odd]; only the epilogue's row -> column map changes.  Same bytes, same DMMA work.
-
+// so A is split into its even and its odd columns.  A class whose columns start 16-byte aligned gets its own tensor map; a
+// class that starts at 8 mod 16 cannot be read by TMA at all (every box would start at an address that is 8 mod 16, which
+// the unit rejects: measured, "illegal instruction"), so the producer warp copies it with 8-byte cp.async (LDGSTS) into the
+// same swizzled layout and signals the stage's mbarrier with cp.async.mbarrier.arrive.  K1: the 16 reduction indices of a
+// stage land as smem lines [k even | k odd]; the consumers pair line L with X row k(L) = L < 8 ? 2L : 2(L-8)+1.  K2: the
+// 128 tile columns land as smem rows [even | odd]; only the epilogue's row -> column map changes.  Same bytes, same DMMA work.
 template <int NB> struct SmemCfg {
   static constexpr uint32_t X_BYTES = NB * 8 * BK * 8;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + X_BYTES;
@@ -79,7 +83,7 @@ k_gemm_an(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], SPLIT ? 33 : 1); mbar_init(&empty[s], NCONS); }   // SPLIT: + one cp.async arrival per producer lane
     fence_mbar_init();
   }
   __syncthreads();
@@ -89,6 +93,48 @@ k_gemm_an(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   if (warp == NCONS) {
     // ---------------- TMA producer ----------------
+    if (SPLIT) {
+      // all 32 lanes: lane 0 issues the TMA loads (X, and the A class(es) that TMA can address), every lane copies its share
+      // of the other class(es) with cp.async and arrives on the stage barrier when its copies have landed
+      if (lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmX); }
+      const uint32_t tma_bytes = SmemCfg<NB>::X_BYTES + (p.sh0 ? 0u : A_BYTES / 2) + (p.sh1 ? 0u : A_BYTES / 2);
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int tile = u / p.nsplit, split = u - tile * p.nsplit;
+        const int k0 = split * p.kchunk, k1 = min(p.K, k0 + p.kchunk);
+        const int m0 = tile * BM;
+        for (int k = k0; k < k1; k += BK) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * STAGE;
+          if (lane == 0) {
+            mbar_expect_tx(&full[stage], tma_bytes);
+#pragma unroll
+            for (int b = 0; b < NCONS; ++b) {
+              if (!p.sh0) tma_load_2d(sa + b * (16 * BK * 8), &tmA, &full[stage], m0 + 16 * b, k >> 1);            // lines 0-7: k even
+              if (!p.sh1) tma_load_2d(sa + b * (16 * BK * 8) + 1024, &tmA1, &full[stage], m0 + 16 * b, k >> 1);    // lines 8-15: k odd
+            }
+            tma_load_2d(sa + A_BYTES, &tmX, &full[stage], k, 0);
+          }
+#pragma unroll
+          for (int cls = 0; cls < 2; ++cls) {
+            if (cls ? p.sh1 : p.sh0) {
+              // 8 boxes x 8 lines x 16 rows = 1024 elements per class; element e = lane + 32 q: row i = lane & 15, line kk = (lane >> 4) + 2 (q & 3), box b = q >> 2
+              const int li = lane & 15, lj = lane >> 4;
+              const double* base = p.Araw + (size_t)(k + cls + 2 * lj) * p.lda + m0 + li;
+              const size_t step = (size_t)4 * p.lda;
+#pragma unroll
+              for (int q = 0; q < 32; ++q) {
+                const int kk = lj + 2 * (q & 3), b = q >> 2;
+                const bool ok = (k + 2 * kk + cls) < p.K && (m0 + 16 * b + li) < p.M;
+                const double* src = ok ? base + (q & 3) * step + 16 * b : p.Araw;
+                cp_async_8(sa + b * (16 * BK * 8) + cls * 1024 + kk * 128 + (((li >> 1) ^ kk) << 4) + (li & 1) * 8, src, ok ? 8u : 0u);
+              }
+            }
+          }
+          cp_async_mbar_arrive_noinc(&full[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else
     if (lane == 0) {
       tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmX);
       for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -99,16 +145,8 @@ k_gemm_an(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE);
           uint8_t* sa = smem + (size_t)stage * STAGE;
-          if (SPLIT) {
 #pragma unroll
-            for (int b = 0; b < NCONS; ++b) {
-              tma_load_2d(sa + b * (16 * BK * 8), &tmA, &full[stage], m0 + 16 * b + p.sh0, k >> 1);            // lines 0-7: k even
-              tma_load_2d(sa + b * (16 * BK * 8) + 1024, &tmA1, &full[stage], m0 + 16 * b + p.sh1, k >> 1);    // lines 8-15: k odd
-            }
-          } else {
-#pragma unroll
-            for (int b = 0; b < NCONS; ++b) tma_load_2d(sa + b * (16 * BK * 8), &tmA, &full[stage], m0 + 16 * b, k);
-          }
+          for (int b = 0; b < NCONS; ++b) tma_load_2d(sa + b * (16 * BK * 8), &tmA, &full[stage], m0 + 16 * b, k);
           tma_load_2d(sa + A_BYTES, &tmX, &full[stage], k, 0);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -207,7 +245,7 @@ k_gemm_at(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], SPLIT ? 33 : 1); mbar_init(&empty[s], NCONS); }   // SPLIT: + one cp.async arrival per producer lane
     fence_mbar_init();
   }
   __syncthreads();
@@ -216,6 +254,44 @@ k_gemm_at(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   int stage = 0; uint32_t phase = 0;
 
   if (warp == NCONS) {
+    if (SPLIT) {
+      if (lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmQ); }
+      const uint32_t tma_bytes = SmemCfg<NB>::X_BYTES + (p.sh0 ? 0u : A_BYTES / 2) + (p.sh1 ? 0u : A_BYTES / 2);
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int tile = u / p.nsplit, split = u - tile * p.nsplit;
+        const int k0 = split * p.kchunk, k1 = min(p.K, k0 + p.kchunk);
+        const int j0 = tile * BM;
+        for (int k = k0; k < k1; k += BK) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * STAGE;
+          if (lane == 0) {
+            mbar_expect_tx(&full[stage], tma_bytes);
+            if (!p.sh0) tma_load_2d(sa, &tmA, &full[stage], k, j0 >> 1);                 // smem rows 0-63: even tile columns
+            if (!p.sh1) tma_load_2d(sa + 64 * 128, &tmA1, &full[stage], k, j0 >> 1);     // smem rows 64-127: odd tile columns
+            tma_load_2d(sa + A_BYTES, &tmQ, &full[stage], k, 0);
+          }
+#pragma unroll
+          for (int cls = 0; cls < 2; ++cls) {
+            if (cls ? p.sh1 : p.sh0) {
+              // 64 columns x 16 reduction indices per class; element e = lane + 32 q: k offset i = lane & 15, column jj = (lane >> 4) + 2 q
+              const int li = lane & 15, lj = lane >> 4;
+              const double* base = p.Araw + (size_t)(j0 + cls + 2 * lj) * p.lda + k + li;
+              const size_t step = (size_t)4 * p.lda;
+              const bool kok = (k + li) < p.K;
+#pragma unroll
+              for (int q = 0; q < 32; ++q) {
+                const int jj = lj + 2 * q, R = 64 * cls + jj;
+                const bool ok = kok && (j0 + 2 * jj + cls) < p.M;
+                const double* src = ok ? base + q * step : p.Araw;
+                cp_async_8(sa + R * 128 + (((li >> 1) ^ (R & 7)) << 4) + (li & 1) * 8, src, ok ? 8u : 0u);
+              }
+            }
+          }
+          cp_async_mbar_arrive_noinc(&full[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else
     if (lane == 0) {
       tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmQ);
       for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -226,12 +302,7 @@ k_gemm_at(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE);
           uint8_t* sa = smem + (size_t)stage * STAGE;
-          if (SPLIT) {
-            tma_load_2d(sa, &tmA, &full[stage], k + p.sh0, j0 >> 1);                 // smem rows 0-63: even tile columns
-            tma_load_2d(sa + 64 * 128, &tmA1, &full[stage], k + p.sh1, j0 >> 1);     // smem rows 64-127: odd tile columns
-          } else {
-            tma_load_2d(sa, &tmA, &full[stage], k, j0);
-          }
+          tma_load_2d(sa, &tmA, &full[stage], k, j0);
           tma_load_2d(sa + A_BYTES, &tmQ, &full[stage], k, 0);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -467,13 +538,22 @@ template <int NB, bool SPLIT> cudaError_t launch_at(const CUtensorMap& tA, const
     case 15: e = FN<15, SPL>(__VA_ARGS__); break; default: e = FN<16, SPL>(__VA_ARGS__); break;                           \
   }
 
-// A that one tensor map cannot describe: two maps over the columns of each parity (see the SPLIT note above GemmParams).
-// rows x cols matrix, column stride lda; box {16, box_cols}.  Returns false when a class would be empty (cols < 2).
+// A that one tensor map cannot describe: one map per column parity where that class starts 16-byte aligned; sh = 1 marks a
+// class that starts at 8 mod 16 and is copied with cp.async instead (its map slot gets a valid dummy).
+// rows x cols matrix, column stride lda; box {16, box_cols}.  Returns false when there are fewer than two columns.
 bool make_split_maps(CUtensorMap* m0, CUtensorMap* m1, int* sh0, int* sh1, const double* A, long long rows, long long cols, long long lda, int box_cols) {
   if (cols < 2) return false;
   const double* a0 = A; const double* a1 = A + lda;
   *sh0 = (int)((reinterpret_cast<uintptr_t>(a0) >> 3) & 1); *sh1 = (int)((reinterpret_cast<uintptr_t>(a1) >> 3) & 1);
-  return make_map(m0, a0 - *sh0, rows + *sh0, (cols + 1) / 2, 2 * lda, box_cols) && make_map(m1, a1 - *sh1, rows + *sh1, cols / 2, 2 * lda, box_cols);
+  bool ok = true;
+  if (!*sh0) ok = ok && make_map(m0, a0, rows, (cols + 1) / 2, 2 * lda, box_cols);
+  if (!*sh1) ok = ok && make_map(m1, a1, rows, cols / 2, 2 * lda, box_cols);
+  if (*sh0 && !*sh1) *m0 = *m1;
+  if (*sh1 && !*sh0) *m1 = *m0;
+  if (*sh0 && *sh1) {                        // both classes by cp.async: any valid descriptor (over the aligned element after A)
+    ok = make_map(m0, A + 1, rows > 1 ? rows - 1 : 1, 1, 2 * lda, box_cols); *m1 = *m0;
+  }
+  return ok;
 }
 
 // the skinny operand (K x N) is small: when IT is not TMA-addressable it is repacked into an even-ld scratch
@@ -535,7 +615,7 @@ cudaError_t gemm_an(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
     CUtensorMap tX;
     if (!make_map(&tX, X + (size_t)n0 * ldx, K, nc, ldx, NB * 8)) return cudaErrorInvalidValue;
     GemmParams p{};
-    p.M = (int)M; p.N = nc; p.K = (int)K; p.ntiles = ntiles; p.nsplit = nsplit; p.kchunk = kchunk; p.transpose_out = 0; p.sh0 = sh0; p.sh1 = sh1;
+    p.M = (int)M; p.N = nc; p.K = (int)K; p.ntiles = ntiles; p.nsplit = nsplit; p.kchunk = kchunk; p.transpose_out = 0; p.sh0 = sh0; p.sh1 = sh1; p.Araw = A; p.lda = lda;
     double* yout = Y + (size_t)n0 * ldy;
     if (nsplit == 1) {
       p.out = yout; p.ld_out = ldy; p.split_stride = 0;
@@ -595,7 +675,7 @@ cudaError_t gemm_at(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
     CUtensorMap tQ;
     if (!make_map(&tQ, Q + (size_t)n0 * ldq, K, nc, ldq, NB * 8)) return cudaErrorInvalidValue;
     GemmParams p{};
-    p.M = (int)M; p.N = nc; p.K = (int)K; p.ntiles = ntiles; p.nsplit = nsplit; p.kchunk = kchunk; p.vec_ok = 0; p.sh0 = sh0; p.sh1 = sh1;
+    p.M = (int)M; p.N = nc; p.K = (int)K; p.ntiles = ntiles; p.nsplit = nsplit; p.kchunk = kchunk; p.vec_ok = 0; p.sh0 = sh0; p.sh1 = sh1; p.Araw = A; p.lda = lda;
     double* zout = transpose_out ? Z + n0 : Z + (size_t)n0 * ldz;
     if (nsplit == 1) {
       p.out = zout; p.ld_out = ldz; p.split_stride = 0; p.transpose_out = transpose_out;

@@ -42,6 +42,16 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// 8-byte asynchronous copy global -> shared (SASS LDGSTS); src_bytes == 0 writes zeros without touching global memory.
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+// One arrival on `bar` once all cp.async issued so far by this thread have landed (the arrival is part of the barrier's
+// expected count: .noinc).
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // D(16x8) += A(16x4) * B(4x8), FP64, SASS DMMA.  Fragment ownership (PTX ISA, mma.m16n8k4 .f64), g = lane>>2, t = lane&3:
 //   a0 = A[g][t], a1 = A[g+8][t];  b0 = B[t][g];  c0,c1 = C[g][2t],C[g][2t+1];  c2,c3 = C[g+8][2t],C[g+8][2t+1].
 __device__ __forceinline__ void dmma_16x8x4(double (&c)[4], double a0, double a1, double b0) {
