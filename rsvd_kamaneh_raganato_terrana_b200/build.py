@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             print(out)
     if failed:
         raise RuntimeError("librsvdb.so build failed")
-    cmd = [_nvcc(), "-shared", "-ccbin", "/usr/bin/g++", "-o", str(LIB), *objs, "-lcudart", "-ldl"]
+    cmd = [_nvcc(), "-shared", "-ccbin", "/usr/bin/g++", "-o", str(LIB), *objs, "-lcudart", "-ldl", "-lpthread"]
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("librsvdb.so link failed:\n" + r.stdout)

@@ -52,11 +52,7 @@ __global__ void k_reciprocal(const double* __restrict__ x, double* __restrict__ 
 int h2d(rsvdb_ctx* c, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
   if (rows <= 0 || cols <= 0) return 0;
   PhaseTimer pt(c, PH_COPY);
-  if (ldd == rows && lds == rows) {
-    RSVDB_CUDA(c, cudaMemcpyAsync(dst, src, (size_t)rows * cols * 8, cudaMemcpyHostToDevice, c->stream));
-  } else {
-    RSVDB_CUDA(c, cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyHostToDevice, c->stream));
-  }
+  RSVDB_CUDA(c, upload_block(c, c->stream, dst, ldd, src, lds, rows, cols));
   return 0;
 }
 int d2h(rsvdb_ctx* c, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
@@ -124,6 +120,7 @@ int rsvdb_destroy(rsvdb_ctx* c) {
   for (auto& s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (auto e : c->event_pool) cudaEventDestroy(e);
   c->gemm_ws.release(); c->qr_ws.release(); c->qr2_ws.release(); c->tmp_ws.release(); c->svd_ws.release(); c->io_ws.release(); c->wide_ws.release(); c->pca_ws.release(); c->pod_ws.release();
+  delete c->stager;
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return RSVDB_OK;

@@ -5,6 +5,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "gemm_dmma.cuh"
+#include "host_stage.cuh"
 
 enum RsvdbPhase { PH_GEMM_AN = 0, PH_GEMM_AT = 1, PH_QR = 2, PH_SMALL_SVD = 3, PH_COMM = 4, PH_OTHER = 5, PH_COPY = 6, PH_COUNT = 7 };
 
@@ -35,9 +36,20 @@ struct rsvdb_ctx {
   std::vector<Span> spans;
   std::vector<cudaEvent_t> event_pool;
   const int* d_svd_info = nullptr;   // device {sweeps, rotations} of the last Jacobi SVD
+  rsvdb::HostStager* stager = nullptr;   // pinned ring + worker threads for uploads from pageable host memory (lazy)
 };
 
 namespace rsvdb {
+// host -> device copy of a column-major block on `st`: pageable sources of at least 32 MB go through the pinned staging ring
+inline cudaError_t upload_block(rsvdb_ctx* c, cudaStream_t st, double* dst, long long ldd, const double* src, long long lds, long long rows, long long cols) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  if ((size_t)rows * (size_t)cols * sizeof(double) >= (32u << 20) && HostStager::pageable(src)) {
+    if (!c->stager) c->stager = new HostStager();
+    return c->stager->upload(st, dst, ldd, src, lds, rows, cols);
+  }
+  if (ldd == rows && lds == rows) return cudaMemcpyAsync(dst, src, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, st);
+  return cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyHostToDevice, st);
+}
 inline int fail(rsvdb_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
 inline int cuda_fail(rsvdb_ctx* c, cudaError_t e, const char* where) {
   if (c) c->err = std::string(where) + ": " + cudaGetErrorString(e);

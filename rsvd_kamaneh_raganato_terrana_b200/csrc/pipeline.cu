@@ -252,12 +252,7 @@ static int upload_and_first_pass(rsvdb_ctx* c, double* A, int64_t m, int64_t n, 
   int b = 0;
   for (int64_t r0 = 0; r0 < m; r0 += rows_b, ++b) {
     const int64_t r = std::min(rows_b, m - r0);
-    if (r == m && lda == m && up.lda == m) {
-      RSVDB_CUDA(c, cudaMemcpyAsync(A, up.A, bytes, cudaMemcpyHostToDevice, c->side_stream));
-    } else {
-      RSVDB_CUDA(c, cudaMemcpy2DAsync(A + r0, (size_t)lda * 8, up.A + r0, (size_t)up.lda * 8, (size_t)r * 8, (size_t)n,
-                                      cudaMemcpyHostToDevice, c->side_stream));
-    }
+    RSVDB_CUDA(c, upload_block(c, c->side_stream, A + r0, lda, up.A + r0, up.lda, r, n));   // pageable sources: pinned staging ring
     RSVDB_CUDA(c, cudaEventRecord(c->side_ev[b], c->side_stream));
     RSVDB_CUDA(c, cudaStreamWaitEvent(c->stream, c->side_ev[b], 0));
     RSVDB_TRY(gemm_an_phase(c, A + r0, r, n, lda, Omega, ldo, l, Q + r0, ldq));
