@@ -120,6 +120,11 @@ class ClockSampler:
                 "samples": len(rows), "samples_under_load": len(busy) if busy is not rows else 0, "reasons": reasons}
 
 
+def workload_name(m, n, l, q):
+    """The same string in both arms: BASELINE.json configs[4]."""
+    return f"c5: rSVD rank-{l} q={q} of synthetic {m}x{n} FP64, Jacobi back-end, host-supplied Omega"
+
+
 def flops(m, n, l, q):
     return (2 * q + 2) * 2.0 * m * n * l          # SURVEY.md 8d: GEMM passes only (QR, small SVD, U = Q*Ut are overhead)
 
@@ -207,7 +212,8 @@ def run_reference(args):
         "impl": "reference", "metric": "rsvd_gflops", "value": round(g, 2), "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": done,
         "warmup": warm, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"c5: rSVD rank-{l} q={q} of synthetic {m}x{n} FP64 (Jacobi back-end, host Omega)", "m": m, "n": n, "l": l, "q": q,
+        "config": {"workload": workload_name(m, n, l, q), "m": m, "n": n, "l": l, "q": q,
+                   "parallelism": "host cores (the reference replicates the whole computation on every MPI rank)",
                    "steps_requested": args.steps, "warmup_requested": args.warmup},
         "cpu_baseline": {"value": round(g, 2), "unit": "GFLOP/s", "cores": threads, "kind": "port",
                          "host_cpus_available": _host_threads(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
@@ -366,7 +372,7 @@ def run_ours(args):
             "metric": "rsvd_gflops", "value": round(value, 2), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"c5: rSVD rank-{l} q={q} of synthetic {m}x{n} FP64, row-sharded over {world} GPU(s), Jacobi back-end, host-supplied Omega",
+            "config": {"workload": workload_name(m, n, l, q),
                        "m": m, "n": n, "l": l, "q": q, "rows_per_gpu": rows, "parallelism": f"row-shard x{world}",
                        "l2": "inputs larger than L2 (A shard is %.1f GB)" % (rows * n * 8 / 1e9), "time_to_rank_k_ms": round(ms_per_step, 3)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
