@@ -1,6 +1,9 @@
 #include "host_stage.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstring>
 #include <functional>
@@ -118,11 +121,16 @@ cudaError_t HostStager::upload(cudaStream_t st, double* dst, long long ldd, cons
   const long long rt = std::min(rows, chunk_elems);                       // rows per tile
   const long long ct = std::max<long long>(1, chunk_elems / rt);          // columns per tile
   int slot = 0;
+  static const bool debug = getenv("RSVDB_STAGE_DEBUG") != nullptr;
+  double t_wait = 0, t_pack = 0, t_issue = 0; int ntiles = 0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (long long r0 = 0; r0 < rows; r0 += rt) {
     const long long nr = std::min(rt, rows - r0);
     for (long long c0 = 0; c0 < cols; c0 += ct) {
       const long long nc = std::min(ct, cols - c0);
+      double t0 = debug ? now() : 0.0;
       if (p_->busy[slot]) { e = cudaEventSynchronize(p_->ev[slot]); if (e != cudaSuccess) return e; p_->busy[slot] = false; }
+      double t1 = debug ? now() : 0.0;
       double* b = p_->buf[slot];
       const double* s0 = src + r0 + c0 * lds;
       // pack the tile (leading dimension nr): split by columns, or by row ranges when the tile is a few long columns
@@ -139,14 +147,18 @@ cudaError_t HostStager::upload(cudaStream_t st, double* dst, long long ldd, cons
           if (z > a) for (long long c = 0; c < nc; ++c) std::memcpy(b + c * nr + a, s0 + c * lds + a, (size_t)(z - a) * sizeof(double));
         });
       }
+      double t2 = debug ? now() : 0.0;
       e = cudaMemcpy2DAsync(dst + r0 + c0 * ldd, (size_t)ldd * sizeof(double), b, (size_t)nr * sizeof(double), (size_t)nr * sizeof(double), (size_t)nc,
                             cudaMemcpyHostToDevice, st);
       if (e != cudaSuccess) return e;
       e = cudaEventRecord(p_->ev[slot], st); if (e != cudaSuccess) return e;
       p_->busy[slot] = true;
+      if (debug) { const double t3 = now(); t_wait += t1 - t0; t_pack += t2 - t1; t_issue += t3 - t2; ++ntiles; }
       slot = (slot + 1) % kRing;
     }
   }
+  if (debug) std::fprintf(stderr, "[rsvdb stage] %lld x %lld (lds %lld): %d tiles, wait %.2f ms, pack %.2f ms, issue %.2f ms, threads %d\n", rows, cols, lds,
+                          ntiles, t_wait * 1e3, t_pack * 1e3, t_issue * 1e3, p_->nthreads);
   return cudaSuccess;
 }
 
