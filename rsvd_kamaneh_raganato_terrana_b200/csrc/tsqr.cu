@@ -887,6 +887,7 @@ int pick_br(int l) {
   return 0;
 }
 
+int cl0_max_nodes() { static int m = -1; if (m < 0) { const char* e = getenv("RSVDB_TSQR_CL0_MAX"); m = e ? atoi(e) : 16; } return m; }
 int cl_max_nodes() { static int m = -1; if (m < 0) { const char* e = getenv("RSVDB_TSQR_CL_MAX"); m = e ? atoi(e) : 99; } return m; }
 
 size_t blk_smem_bytes(int l) { return ((size_t)(l + 8) * (256 + 4) + 64 + 720 + (size_t)l) * sizeof(double); }
@@ -898,9 +899,13 @@ cudaError_t set_attr_blk_once() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_house_factor_la<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_node_factor_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(k_node_factor_cl<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_node_apply_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(k_node_apply_cl<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_node_factor_cl<CL0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_node_apply_cl<CL0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   done.set();
   return cudaSuccess;
@@ -932,15 +937,22 @@ cudaError_t Tsqr::plan(long long rows, int l) {
     off_top_ = need; need += (size_t)l * l;
     off_scratch_ = need; need += (size_t)std::max<long long>(r, 1) * l;   // apply_global cannot run in place
   } else {
-    const bool use_cl = blk_ && cl_factor_smem(l) <= 227 * 1024 && cl_apply_smem(l) <= 227 * 1024;
+    const bool use_cl = blk_ && cl_factor_smem(l, CL0) <= 227 * 1024 && cl_apply_smem(l) <= 227 * 1024;
     for (;;) {
       Level L; L.rows = r;
       // leaves: 256-row single-CTA blocks (all SMs busy); upper levels and mid-sized panels: 1024-row cluster nodes
       // cluster nodes pay off when the level is latency-bound (few nodes); a level with hundreds of nodes is
       // throughput-bound and runs better as independent 256-row blocks
       const long long nb_cl = (r + CL_ROWS - 1) / CL_ROWS;
-      L.cl = use_cl && r > 256 && nb_cl <= cl_max_nodes() && (!levels_.empty() || r <= CL_ROWS);
-      L.node_rows = L.cl ? CL_ROWS : br_;
+      const long long nb_cl0 = (r + CL0_ROWS - 1) / CL0_ROWS;
+      L.cl = (use_cl && r > 256 && nb_cl <= cl_max_nodes() && (!levels_.empty() || r <= CL_ROWS)) ? CL : 0;
+      // Level 0 as 2048-row nodes (8-CTA clusters) exactly where that removes a tree level: the R stack of the 8-CTA nodes fits ONE
+      // 4-CTA node while the R stack of 256-row leaves would not (l = 100: 2621 < rows <= 20480, e.g. the 20000 x 100 panels of A^T Q:
+      // 10 nodes -> 1 node instead of 79 leaves -> 8 nodes -> 1 node).  Measured (profiles/r02_tsqr_experiments.txt): an 8-CTA node
+      // level costs ~317 us against 134 (leaves) + 219 (4-CTA nodes), so it only pays when a whole level disappears.
+      const long long n_leaves = (r + br_ - 1) / br_;
+      if (use_cl && levels_.empty() && r > CL_ROWS && nb_cl0 <= cl0_max_nodes() && n_leaves * l > CL_ROWS && nb_cl0 * l <= CL_ROWS) L.cl = CL0;
+      L.node_rows = L.cl ? L.cl * 256 : br_;
       L.nb = (int)((r + L.node_rows - 1) / L.node_rows);
       L.off_R = need; need += (size_t)L.nb * l * l;
       L.off_tau = need; need += (size_t)L.nb * l;
@@ -973,8 +985,10 @@ cudaError_t Tsqr::factor(cudaStream_t st, double* Y, long long ldy, int* launche
     cudaError_t e;
     if (blk_) {
       e = set_attr_blk_once(); if (e != cudaSuccess) return e;
-      if (L.cl)
-        k_node_factor_cl<<<L.nb * CL, BQ_THREADS, cl_factor_smem(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
+      if (L.cl == CL0)
+        k_node_factor_cl<CL0><<<L.nb * CL0, BQ_THREADS, cl_factor_smem(l_, CL0), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
+      else if (L.cl)
+        k_node_factor_cl<CL><<<L.nb * CL, BQ_THREADS, cl_factor_smem(l_, CL), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
       else
         k_house_factor_la<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), st>>>(cur, ld, L.rows, l_, base + L.off_tau, base + L.off_R, ldr, base + L.off_T);
     } else
@@ -996,7 +1010,7 @@ cudaError_t Tsqr::factor(cudaStream_t st, double* Y, long long ldy, int* launche
       ApplyTable tab; tab.n = 1;
       tab.lv[0].V = cur; tab.lv[0].ldv = ld; tab.lv[0].rows = L.rows; tab.lv[0].Tg = base + L.off_T; tab.lv[0].Ctop = nullptr; tab.lv[0].ldc = 0;
       tab.lv[0].Q = cur; tab.lv[0].ldq = ld; tab.lv[0].first_block = 0;
-      if (L.cl) k_node_apply_cl<<<L.nb * CL, BQ_THREADS, cl_apply_smem(l_), side_>>>(tab, l_);
+      if (L.cl) k_node_apply_cl<CL><<<L.nb * CL, BQ_THREADS, cl_apply_smem(l_), side_>>>(tab, l_);      // upper levels are never CL0
       else k_house_apply_blk<256><<<L.nb, BQ_THREADS, blk_smem_bytes(l_), side_>>>(tab, l_);
       e = cudaGetLastError(); if (e != cudaSuccess) return e;
       if (launches) ++*launches;
@@ -1033,7 +1047,7 @@ cudaError_t Tsqr::form_q(cudaStream_t st, double* Y, long long ldy, const double
       if (i == 0) { *V = Y; *ldv = ldy; } else { *V = base + levels_[i - 1].off_R; *ldv = (long long)levels_[i - 1].nb * l_; }
     };
     // launch the levels listed in `which` (all of one kind) in one grid
-    auto launch_apply = [&](const std::vector<int>& which, bool cl, const double* C0, long long ldc0) -> cudaError_t {
+    auto launch_apply = [&](const std::vector<int>& which, int cl, const double* C0, long long ldc0) -> cudaError_t {
       if (which.empty()) return cudaSuccess;
       if (which.size() > 16) return cudaErrorInvalidValue;
       ApplyTable tab; tab.n = 0; int first = 0;
@@ -1041,9 +1055,10 @@ cudaError_t Tsqr::form_q(cudaStream_t st, double* Y, long long ldy, const double
         double* V; long long ldv; level_V(i, &V, &ldv);
         ApplyLevel& a = tab.lv[tab.n++];
         a.V = V; a.ldv = ldv; a.rows = levels_[i].rows; a.Tg = base + levels_[i].off_T; a.Ctop = C0; a.ldc = ldc0; a.Q = V; a.ldq = ldv;
-        a.first_block = first; first += levels_[i].nb * (cl ? CL : 1);
+        a.first_block = first; first += levels_[i].nb * (cl ? cl : 1);
       }
-      if (cl) k_node_apply_cl<<<first, BQ_THREADS, cl_apply_smem(l_), st>>>(tab, l_);
+      if (cl == CL0) k_node_apply_cl<CL0><<<first, BQ_THREADS, cl_apply_smem(l_), st>>>(tab, l_);
+      else if (cl) k_node_apply_cl<CL><<<first, BQ_THREADS, cl_apply_smem(l_), st>>>(tab, l_);
       else k_house_apply_blk<256><<<first, BQ_THREADS, smem, st>>>(tab, l_);
       if (launches) ++*launches;
       return cudaGetLastError();
@@ -1056,8 +1071,8 @@ cudaError_t Tsqr::form_q(cudaStream_t st, double* Y, long long ldy, const double
       cudaError_t e = cudaSuccess;
       if (upper_done_) { e = cudaStreamWaitEvent(st, ev_[16], 0); if (e != cudaSuccess) return e; }   // formed on the side stream during factor()
       else {
-        e = launch_apply(up_cl, true, nullptr, 0); if (e != cudaSuccess) return e;
-        e = launch_apply(up_sc, false, nullptr, 0); if (e != cudaSuccess) return e;
+        e = launch_apply(up_cl, CL, nullptr, 0); if (e != cudaSuccess) return e;
+        e = launch_apply(up_sc, 0, nullptr, 0); if (e != cudaSuccess) return e;
       }
       // (B) chain top-down: E_i[node b] = N_i[node b] * E_{i+1}[rows b*l .. (b+1)*l)   (E_top = N_top * Ctop)
       static DevOnce ng_attr;

@@ -22,7 +22,7 @@ class Tsqr {
   int depth() const { return (int)levels_.size(); }
 
  private:
-  struct Level { long long rows; int nb; size_t off_R; size_t off_tau; size_t off_T; size_t off_E; bool cl; int node_rows; };
+  struct Level { long long rows; int nb; size_t off_R; size_t off_tau; size_t off_T; size_t off_E; int cl; int node_rows; };   // cl: CTAs per cluster node (0 = single-CTA blocks)
   GemmWorkspace* ws_;
   cudaStream_t side_ = nullptr;        // optional: upper-level explicit factors are formed here, overlapping the factor chain
   cudaEvent_t* ev_ = nullptr;          // >= 17 events

@@ -10,8 +10,10 @@
 // GPUs) hold bit-identical T, tau and W.
 #pragma once
 
-constexpr int CL = 4;                               // CTAs per cluster node
+constexpr int CL = 4;                               // CTAs per cluster node of the upper tree levels
 constexpr int CL_ROWS = CL * 256;
+constexpr int CL0 = 8;                              // CTAs per cluster node at level 0 of panels of <= 16 such nodes (round 2): 2048 rows per node,
+constexpr int CL0_ROWS = CL0 * 256;                 // i.e. one tree level fewer for the 20000- / 25000-row panels of the 8-GPU run
 
 __device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -60,19 +62,20 @@ __device__ __forceinline__ double clean_v_cl(const double* S, const double* Vtop
 
 // shared-memory scratch of a cluster node (doubles): see the carve-up in the kernels
 //   red 64 | drow 8 | xch 2*16*CL | Gtot 64 | xw 16*64 (aliases the per-warp Gram partials 8*64 and the CTA Gram partial 64)
-constexpr int CLS_RED = 0, CLS_DROW = 64, CLS_XCH = 72, CLS_GTOT = CLS_XCH + 2 * 16 * CL, CLS_XW = CLS_GTOT + 64, CLS_TOTAL = CLS_XW + 16 * 64;
+template <int CLT> struct Cls { static constexpr int RED = 0, DROW = 64, XCH = 72, GTOT = XCH + 2 * 16 * CLT, XW = GTOT + 64, TOTAL = XW + 16 * 64; };
 
 // All CTAs of the cluster factor the panel [c0, c0+pb) together.  Every thread of every CTA must call this (non-row
 // warps only take part in the cluster barriers).  Outputs as panel_factor_la; T / tau are identical in all CTAs.
 // Per reflector the 8 column products (+ the diagonal row, from rank 0) of every CTA go to every CTA with st.async and are
 // awaited on a local mbarrier by the row team only (xbar[2], alternating per reflector; xphase tracks their parities): ncu
 // showed barrier.cluster per reflector -- 2048 threads arriving 100 times per node -- as the top stall of the round-1 kernel.
+template <int CLT>
 __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double* Tsm, double* tau_s, double* Tglob, double* sc,
                                                 int c0, int pb, int warp, int lane, unsigned rank, uint64_t* xbar, uint32_t& xphase) {
   constexpr int LDS = 256 + 4;
-  double* red = sc + CLS_RED; double* drow = sc + CLS_DROW; double* xch = sc + CLS_XCH; double* Gtot = sc + CLS_GTOT;
-  double* Gs = sc + CLS_XW;                      // [8 warps][64] during the Gram step
-  double* Gcta = sc + CLS_XW + 8 * 64;           // [64] this CTA's Gram partial (read remotely)
+  double* red = sc + Cls<CLT>::RED; double* drow = sc + Cls<CLT>::DROW; double* xch = sc + Cls<CLT>::XCH; double* Gtot = sc + Cls<CLT>::GTOT;
+  double* Gs = sc + Cls<CLT>::XW;                // [8 warps][64] during the Gram step
+  double* Gcta = sc + Cls<CLT>::XW + 8 * 64;     // [64] this CTA's Gram partial (read remotely)
   const bool roww = warp < BQ_ROW_WARPS;
   const int i = roww ? 32 * warp + lane : 0;
   const int gi = (int)rank * 256 + i;            // node row index
@@ -99,16 +102,16 @@ __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double*
           for (int c = 0; c < 8; ++c) drow[c] = a[c];
         }
         bar_rows();
-        if (warp == 0 && lane == 0) mbar_expect_tx(&xbar[b], CL * 16 * 8);   // this round: 16 doubles from each CTA of the cluster
+        if (warp == 0 && lane == 0) mbar_expect_tx(&xbar[b], CLT * 16 * 8);   // this round: 16 doubles from each CTA of the cluster
         if (warp == 0 && lane < 16) {            // CTA partial (8 column products) + the diagonal row (from rank 0) to every CTA
           double v;
           if (lane < 8) { v = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) v += red[lane * 8 + w];
           } else v = (rank == 0) ? drow[lane - 8] : 0.0;
-          double* slot = xch + b * 16 * CL + lane * CL + rank;
+          double* slot = xch + b * 16 * CLT + lane * CLT + rank;
 #pragma unroll
-          for (unsigned tr = 0; tr < CL; ++tr) st_async_cluster(slot, tr, v, &xbar[b]);
+          for (unsigned tr = 0; tr < CLT; ++tr) st_async_cluster(slot, tr, v, &xbar[b]);
         }
         mbar_wait_cluster(&xbar[b], (xphase >> b) & 1u);
         xphase ^= (1u << b);
@@ -119,12 +122,14 @@ __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double*
       for (int c = 0; c < 8; ++c) {
         tot[c] = 0.0;
         if (c >= r) {
-          const double2* q = reinterpret_cast<const double2*>(xch + b * 16 * CL + c * CL);
-          const double2 q0 = q[0], q1 = q[1];
-          tot[c] = (q0.x + q0.y) + (q1.x + q1.y);
+          const double2* q = reinterpret_cast<const double2*>(xch + b * 16 * CLT + c * CLT);
+          double t2 = 0.0;
+#pragma unroll
+          for (int h = 0; h < CLT / 2; ++h) { const double2 qq = q[h]; t2 += qq.x + qq.y; }      // rank order, identical on every CTA
+          tot[c] = t2;
         }
       }
-      const double tail = tot[r], x0 = xch[b * 16 * CL + (8 + r) * CL + 0];
+      const double tail = tot[r], x0 = xch[b * 16 * CLT + (8 + r) * CLT + 0];
       double beta, scale;
       if (tail <= DBL_MIN) { tau[r] = 0.0; beta = x0; scale = 0.0; }
       else {
@@ -141,7 +146,7 @@ __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double*
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         if (c > r && c < pb) {
-          const double w = tau[r] * fma(scale, tot[c], xch[b * 16 * CL + (8 + c) * CL + 0]);
+          const double w = tau[r] * fma(scale, tot[c], xch[b * 16 * CLT + (8 + c) * CLT + 0]);
           a[c] = fma(-w, v, a[c]);
         }
       }
@@ -180,7 +185,7 @@ __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double*
   if (threadIdx.x < 64) {
     double s2 = 0.0;
 #pragma unroll
-    for (unsigned sr = 0; sr < CL; ++sr) s2 += ld_cluster(Gcta + threadIdx.x, sr);
+    for (unsigned sr = 0; sr < CLT; ++sr) s2 += ld_cluster(Gcta + threadIdx.x, sr);
     Gtot[threadIdx.x] = s2;
   }
   cluster_sync_all();                               // remote reads of Gcta are done before anyone reuses the xw region
@@ -211,6 +216,7 @@ __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double*
 // Block reflector on the columns [col_begin, col_end) of this CTA's rows, W = V^T C summed over the cluster.
 // Reflectors come either from S in place (Vp == nullptr: factor kernel; + Vtop for the panel's first 8 node rows) or from
 // a staged clean panel Vp (apply kernel).  One group of 8 columns per warp (<= 16 groups).  Every thread must call it.
+template <int CLT>
 __device__ __forceinline__ void block_reflect_cl(double* S, const double* Vp, const double* Vtop, const double* Tsm, double* xw, int c0,
                                                  int col_begin, int col_end, int warp, int lane, unsigned rank, bool transposeT,
                                                  bool second_barrier) {
@@ -247,7 +253,7 @@ __device__ __forceinline__ void block_reflect_cl(double* S, const double* Vp, co
   if (have) {
     w0 = 0.0; w1 = 0.0;
 #pragma unroll
-    for (unsigned sr = 0; sr < CL; ++sr) {
+    for (unsigned sr = 0; sr < CLT; ++sr) {
       w0 += ld_cluster(xw + warp * 64 + g + 8 * (2 * t), sr);
       w1 += ld_cluster(xw + warp * 64 + g + 8 * (2 * t + 1), sr);
     }
@@ -289,7 +295,8 @@ __device__ __forceinline__ void block_reflect_cl(double* S, const double* Vp, co
 }
 
 // Factor one 1024-row node per cluster.  Same outputs as k_house_factor_la: reflectors overwrite Y, tau / T / R per node.
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BQ_THREADS, 1)
+template <int CLT>
+__global__ void __cluster_dims__(CLT, 1, 1) __launch_bounds__(BQ_THREADS, 1)
 k_node_factor_cl(double* __restrict__ Y, long long ldy, long long rows, int l, double* __restrict__ tau_g,
                  double* __restrict__ Rstack, long long ldr, double* __restrict__ Tg) {
   constexpr int LDS = 256 + 4;
@@ -298,13 +305,13 @@ k_node_factor_cl(double* __restrict__ Y, long long ldy, long long rows, int l, d
   double* Vtop = S + (size_t)l * LDS;              // 64
   double* Tsm = Vtop + 64;                         // 64
   double* sc = Tsm + 64;                           // CLS_TOTAL
-  double* tau_s = sc + CLS_TOTAL;
+  double* tau_s = sc + Cls<CLT>::TOTAL;
   uint64_t* xbar = reinterpret_cast<uint64_t*>(tau_s + l);     // 2 mbarriers of the per-reflector exchange
   uint32_t xphase = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned rank = cluster_rank();
-  const int node = blockIdx.x / CL;
-  const long long r0 = (long long)node * CL_ROWS + (long long)rank * 256;
+  const int node = blockIdx.x / CLT;
+  const long long r0 = (long long)node * (CLT * 256) + (long long)rank * 256;
   const int nrows = (int)max(0LL, min(256LL, rows - r0));
   const int npanels = (l + 7) / 8;
 
@@ -318,9 +325,9 @@ k_node_factor_cl(double* __restrict__ Y, long long ldy, long long rows, int l, d
   double* Tblock = (rank == 0) ? Tg + (size_t)node * npanels * 64 : nullptr;
   for (int p = 0; p < npanels; ++p) {
     const int c0 = 8 * p, pb = min(8, l - c0);
-    panel_factor_cl(S, Vtop, Tsm, tau_s, Tblock ? Tblock + (size_t)p * 64 : nullptr, sc, c0, pb, warp, lane, rank, xbar, xphase);
+    panel_factor_cl<CLT>(S, Vtop, Tsm, tau_s, Tblock ? Tblock + (size_t)p * 64 : nullptr, sc, c0, pb, warp, lane, rank, xbar, xphase);
     __syncthreads();
-    if (c0 + pb < l) block_reflect_cl(S, nullptr, Vtop, Tsm, sc + CLS_XW, c0, c0 + pb, l, warp, lane, rank, true, false);
+    if (c0 + pb < l) block_reflect_cl<CLT>(S, nullptr, Vtop, Tsm, sc + Cls<CLT>::XW, c0, c0 + pb, l, warp, lane, rank, true, false);
     __syncthreads();
   }
   for (int k = warp; k < l; k += BQ_WARPS) {
@@ -336,7 +343,8 @@ k_node_factor_cl(double* __restrict__ Y, long long ldy, long long rows, int l, d
 }
 
 // Form Q for cluster nodes: Q_node = H_0 ... H_{l-1} [C; 0], C = rows [node*l, (node+1)*l) of Ctop (or the identity).
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BQ_THREADS, 1)
+template <int CLT>
+__global__ void __cluster_dims__(CLT, 1, 1) __launch_bounds__(BQ_THREADS, 1)
 k_node_apply_cl(const ApplyTable tab, int l) {
   constexpr int LDS = 256 + 4;
   constexpr int VPT = 8 * 256 / BQ_THREADS;
@@ -352,8 +360,8 @@ k_node_apply_cl(const ApplyTable tab, int l) {
   const double* V = tab.lv[li].V; const long long ldv = tab.lv[li].ldv; const long long rows = tab.lv[li].rows;
   const double* Tg = tab.lv[li].Tg; const double* Ctop = tab.lv[li].Ctop; const long long ldc = tab.lv[li].ldc;
   double* Q = tab.lv[li].Q; const long long ldq = tab.lv[li].ldq;
-  const int node = ((int)blockIdx.x - tab.lv[li].first_block) / CL;
-  const long long r0 = (long long)node * CL_ROWS + (long long)rank * 256;
+  const int node = ((int)blockIdx.x - tab.lv[li].first_block) / CLT;
+  const long long r0 = (long long)node * (CLT * 256) + (long long)rank * 256;
   const int nrows = (int)max(0LL, min(256LL, rows - r0));
   const int npanels = (l + 7) / 8;
   const int roff = (int)rank * 256;
@@ -389,7 +397,7 @@ k_node_apply_cl(const ApplyTable tab, int l) {
     if (threadIdx.x < 64) Tsm[threadIdx.x] = Tblock[(size_t)p * 64 + threadIdx.x];
     if (p > 0) fetch(p - 1);
     __syncthreads();
-    block_reflect_cl(S, Vp, nullptr, Tsm, xw, 8 * p, 0, l, warp, lane, rank, false, true);
+    block_reflect_cl<CLT>(S, Vp, nullptr, Tsm, xw, 8 * p, 0, l, warp, lane, rank, false, true);
   }
   __syncthreads();
   for (int k = warp; k < l; k += BQ_WARPS) {
@@ -399,5 +407,5 @@ k_node_apply_cl(const ApplyTable tab, int l) {
   cluster_sync_all();
 }
 
-inline size_t cl_factor_smem(int l) { return ((size_t)l * 260 + 128 + CLS_TOTAL + (size_t)l + 2) * sizeof(double); }
+inline size_t cl_factor_smem(int l, int clt = CL) { return ((size_t)l * 260 + 128 + (72 + 32 * clt + 64 + 16 * 64) + (size_t)l + 2) * sizeof(double); }
 inline size_t cl_apply_smem(int l) { return ((size_t)(l + 8) * 260 + 64 + (size_t)((l + 7) / 8) * 64) * sizeof(double); }

@@ -33,6 +33,6 @@ def run(rows, l, kind="randn", reps=3):
 ok = True
 for rows, l, kind in [(256, 100, "randn"), (200, 100, "randn"), (1000, 100, "randn"), (777, 33, "randn"), (100, 16, "randn"), (5000, 50, "rank5"), (3000, 64, "graded"),
                       (20000, 100, "randn"), (25000, 100, "randn"), (200000, 100, "randn"), (50000, 64, "randn"), (100000, 20, "randn"), (4096, 50, "randn"),
-                      (20000, 103, "randn"), (20000, 104, "randn"), (20000, 128, "randn"), (50000, 200, "randn"), (6000, 150, "rank5"), (8000, 256, "graded"), (5000, 7, "randn"), (64, 64, "randn"), (120, 100, "randn")]:
+                      (1025, 100, "randn"), (2048, 64, "randn"), (2049, 100, "rank5"), (32768, 100, "randn"), (32769, 100, "randn"), (12345, 37, "graded"), (30001, 8, "randn"), (20000, 103, "randn"), (20000, 104, "randn"), (20000, 128, "randn"), (50000, 200, "randn"), (6000, 150, "rank5"), (8000, 256, "graded"), (5000, 7, "randn"), (64, 64, "randn"), (120, 100, "randn")]:
     ok &= run(rows, l, kind)
 print(json.dumps({"all_ok": bool(ok)}))
