@@ -685,6 +685,43 @@ def test_rsvd_csr_full_size_properties(engine):
     assert np.all(np.linalg.norm(AV, axis=0) >= S[:8] * (1 - 1e-12))
 
 
+def test_cpp_sparse_mtx_to_rsvd_without_densifying(tmp_path):
+    """SURVEY 8(f) rank 4 on the C++ side: include/rsvdb_mtx.hpp load_market_csr + rSVD(CsrMatrix, ...) -- a sparse .mtx goes to the CSR
+    SpMM path, never densified; the reference densifies every input (tests/rSVD_test.cpp:54-57).  Checked on the reference's own
+    inputs (identity: sigma = 1, error sqrt(n - 16); the dense rank-2 ramp) and on a random sparse matrix against LAPACK."""
+    import subprocess
+    import scipy.sparse as sp
+    from rsvd_kamaneh_raganato_terrana_b200 import mtx
+    root = Path(__file__).resolve().parent.parent
+    libdir = root / "rsvd_kamaneh_raganato_terrana_b200"
+    exe = tmp_path / "rsvd_csr_mtx_test"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-I", str(root / "include"), "-o", str(exe), str(root / "tests" / "cpp" / "rsvd_csr_mtx_test.cpp"),
+                    "-L", str(libdir), "-lrsvdb", f"-Wl,-rpath,{libdir}"], check=True)
+    def run(path, l):
+        out = subprocess.run([str(exe), str(path), str(l), str(tmp_path / "o")], check=True, capture_output=True, text=True).stdout
+        return float(out.split("norm of diff : ")[1].split()[0]), float(out.split("norm of A : ")[1].split()[0]), out
+    mtx.save_coordinate(tmp_path / "eye140.mtx", W.c1_identity(140), tol=1e-300)
+    err, nA, out = run(tmp_path / "eye140.mtx", 16)
+    assert abs(err - np.sqrt(140 - 16)) < 1e-6 and "nnz: 140" in out and "invalid method throws: 1" in out
+    S = mtx.load_dense(tmp_path / "o_S.mtx").ravel()
+    assert S.shape == (16,) and np.max(np.abs(S - 1.0)) < 1e-12
+    mtx.save_coordinate(tmp_path / "ramp.mtx", W.c1_ramp(100), tol=0.0)
+    err, nA, _ = run(tmp_path / "ramp.mtx", 16)
+    S = mtx.load_dense(tmp_path / "o_S.mtx").ravel()
+    assert err < 1e-7 and abs(S[0] - 5.77391767e5) / 5.77391767e5 < 1e-8 and abs(S[1] - 1.44312761e3) / 1.44312761e3 < 1e-8
+    M = sp.random(3000, 1200, density=0.004, format="coo", random_state=np.random.default_rng(8), data_rvs=np.random.default_rng(9).standard_normal)
+    lowrank = np.random.default_rng(10).standard_normal((3000, 6)) @ np.random.default_rng(11).standard_normal((6, 1200))
+    A = M.toarray() * 1e-3 + np.where(np.abs(lowrank) > 2.5, lowrank, 0.0)                # sparse, with a dominant low-rank-ish part
+    mtx.save_coordinate(tmp_path / "rand.mtx", A, tol=1e-300)
+    err, nA, out = run(tmp_path / "rand.mtx", 40)
+    sv = np.linalg.svd(A, compute_uv=False)
+    S = mtx.load_dense(tmp_path / "o_S.mtx").ravel()
+    assert np.all(S <= sv[:40] * (1 + 1e-10)) and S[0] >= 0.97 * sv[0]                     # Ritz values of a q = 2 range finder from below
+    U = mtx.load_dense(tmp_path / "o_U.mtx"); V = mtx.load_dense(tmp_path / "o_V.mtx")
+    assert U.shape == (3000, 40) and V.shape == (1200, 40)
+    assert abs(err - np.linalg.norm(A - (U * S) @ V.T)) <= 1e-8 * nA and err <= 1.05 * np.sqrt(np.sum(sv[40:] ** 2)) + 0.3 * nA
+
+
 def test_cpp_reference_test_driver(tmp_path):
     """tests/cpp/rsvd_test_main.cpp = the reference's `make test` driver (tests/rSVD_test.cpp) against the drop-in headers,
     run on the reference's five input matrices (regenerated); known answers from BASELINE.md section 3."""
@@ -892,6 +929,14 @@ def test_cpp_older_api_headers(oracle, tmp_path):
                     "-L", str(libdir), "-lrsvdb", f"-Wl,-rpath,{libdir}"], check=True)
     m, n, l = 120, 90, 15                      # image_compression/tests/rSVD_test1.cpp: k = 5, p = 10
     rng = np.random.default_rng(5)
+    # first the input pinned to the reference's own sources (exact rank 8: the answer does not depend on the Omega drawn inside)
+    A8, _ = G1.v1_inputs()["rank8_120x90_l15"]
+    A8.ravel(order="F").tofile(tmp_path / "A8.bin")
+    subprocess.run([str(exe), str(tmp_path / "A8.bin"), str(m), str(n), str(l), str(tmp_path / "g")], check=True, capture_output=True, text=True)
+    Sg = np.fromfile(tmp_path / "g_S.bin"); Sref = GOLD1["v1/rsvd/rank8_120x90_l15/S"]
+    assert np.max(np.abs(Sg[:8] - Sref[:8]) / Sref[:8]) <= 1e-8 and np.all(Sg[8:] <= 1e-10)
+    Ug = np.fromfile(tmp_path / "g_U.bin").reshape((m, l), order="F"); Vg = np.fromfile(tmp_path / "g_V.bin").reshape((n, l), order="F")
+    assert np.linalg.norm(A8 - (Ug * Sg) @ Vg.T) <= float(GOLD1["v1/rsvd/rank8_120x90_l15/err"]) + 1e-10 * np.linalg.norm(A8)
     A = np.asfortranarray(rng.standard_normal((m, 12)) @ np.diag(0.5 ** np.arange(12)) @ rng.standard_normal((12, n)))
     A.ravel(order="F").tofile(tmp_path / "A.bin")
     out = subprocess.run([str(exe), str(tmp_path / "A.bin"), str(m), str(n), str(l), str(tmp_path / "o")], check=True, capture_output=True, text=True).stdout
