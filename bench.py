@@ -308,12 +308,13 @@ def run_ours(args):
     achieved = flops(rows, n, l, q) / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
     traffic = None
     try:   # dram__bytes_read + write of one k_gemm_an launch from the committed ncu --set full capture, scaled to this shard
-        t = json.loads((ROOT / "profiles" / "NCU_TRAFFIC.json").read_text())["k_gemm_an<13>"]
-        traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) * (rows * n) / (200000.0 * 20000.0)
+        tj = json.loads((ROOT / "profiles" / "NCU_TRAFFIC.json").read_text())
+        per = [tj[k]["dram_bytes_read"] + tj[k]["dram_bytes_write"] for k in ("k_gemm_an<13>", "k_gemm_at<13>") if k in tj]
+        traffic = sum(per) / len(per) * (rows * n) / (200000.0 * 20000.0)          # mean over the two kernels (3 launches each per step)
     except Exception:
         pass
     roofline = {"bound": "tensor", "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "traffic_note": "DRAM bytes per GEMM launch (ncu, profiles/r01_ncu_gemm_full_summary.txt); algorithmic bytes per launch = 8*rows*n",
+                "traffic": traffic, "traffic_note": "DRAM bytes per GEMM launch, mean of k_gemm_an / k_gemm_at (ncu --set full, profiles/r02_ncu_full_summary.txt, NCU_TRAFFIC.json), scaled to this shard; algorithmic bytes per launch = 8*rows*n",
                 "algorithmic_bytes_per_launch": 8.0 * rows * n, "kernel": "k_gemm_an<13> / k_gemm_at<13> (FP64 DMMA + TMA), 6 passes per step",
                 "peak_source": peak_src, "gemm_ms_per_step": round(gemm_ms, 3),
                 "whole_step_frac_of_peak": round(value * 1e-3 / (world * peak), 4),
