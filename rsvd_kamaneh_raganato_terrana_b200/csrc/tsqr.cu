@@ -412,15 +412,17 @@ __device__ __forceinline__ void panel_factor_la(double* S, double* Vtop, double*
         for (int c = 0; c < 8; ++c) drow[b * 8 + c] = a[c];
       }
       bar_rows();
+      // cross-warp sum of the 8 x 8 partials: lane L reads ONE 16-byte pair (partials 2L, 2L+1 of column L >> 2), two butterfly
+      // steps finish the column, then the totals are broadcast -- 1 LDS.128 + 10 shuffles instead of 32 LDS.128 + 56 adds per thread
+      // (the read-back of all 64 partials by every thread was 35 % of the panel's ncu samples)
       double tot[8];
+      {
+        const double2 pr = reinterpret_cast<const double2*>(red + b * 64)[lane];
+        double s2 = pr.x + pr.y;
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        tot[c] = 0.0;
-        if (c >= r) {
-          const double2* q = reinterpret_cast<const double2*>(red + b * 64 + c * 8);
-          const double2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-          tot[c] = ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
-        }
+        for (int c = 0; c < 8; ++c) tot[c] = (c >= r) ? __shfl_sync(0xffffffffu, s2, 4 * c) : 0.0;
       }
       const double tail = tot[r], x0 = drow[b * 8 + r];
       double beta, scale;

@@ -117,19 +117,22 @@ __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double*
         xphase ^= (1u << b);
       }
       if (!roww) continue;
-      double tot[8];
+      // 16 slots x CLT rank partials: each lane sums CLT/4 double2 of one slot, one butterfly step completes the
+      // slot (lanes 2s, 2s+1), broadcasts hand it to every row thread; same order on every CTA of the cluster.
+      double tot[8], dr[8];
+      {
+        const double2* q = reinterpret_cast<const double2*>(xch + b * 16 * CLT) + lane * (CLT / 4);
+        double s2 = 0.0;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        tot[c] = 0.0;
-        if (c >= r) {
-          const double2* q = reinterpret_cast<const double2*>(xch + b * 16 * CLT + c * CLT);
-          double t2 = 0.0;
+        for (int h = 0; h < CLT / 4; ++h) { const double2 qq = q[h]; s2 += qq.x + qq.y; }
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
 #pragma unroll
-          for (int h = 0; h < CLT / 2; ++h) { const double2 qq = q[h]; t2 += qq.x + qq.y; }      // rank order, identical on every CTA
-          tot[c] = t2;
+        for (int c = 0; c < 8; ++c) {
+          tot[c] = (c >= r) ? __shfl_sync(0xffffffffu, s2, 2 * c) : 0.0;
+          dr[c] = (c >= r) ? __shfl_sync(0xffffffffu, s2, 2 * (8 + c)) : 0.0;     // only rank 0 sends non-zero
         }
       }
-      const double tail = tot[r], x0 = xch[b * 16 * CLT + (8 + r) * CLT + 0];
+      const double tail = tot[r], x0 = dr[r];
       double beta, scale;
       if (tail <= DBL_MIN) { tau[r] = 0.0; beta = x0; scale = 0.0; }
       else {
@@ -146,7 +149,7 @@ __device__ __forceinline__ void panel_factor_cl(double* S, double* Vtop, double*
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         if (c > r && c < pb) {
-          const double w = tau[r] * fma(scale, tot[c], xch[b * 16 * CLT + (8 + c) * CLT + 0]);
+          const double w = tau[r] * fma(scale, tot[c], dr[c]);
           a[c] = fma(-w, v, a[c]);
         }
       }
