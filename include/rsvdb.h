@@ -64,6 +64,17 @@ RSVDB_API int64_t rsvdb_launch_count(const rsvdb_ctx* ctx);
  * rsvdb_generic_gemm_fallbacks: products that ran on the CUDA-core kernel instead (only a 1-column A that is also misaligned). */
 RSVDB_API int64_t rsvdb_split_gemm_products(void);
 RSVDB_API int64_t rsvdb_generic_gemm_fallbacks(void);
+/* How the sketches of the rSVD path are orthonormalised (the reference: Eigen::HouseholderQR + thin Q, src/rSVD.cpp:60-68 and
+ * the QR preconditioner of include/SVD_class.hpp:110-123).
+ *   policy 0 (default): guarded CholeskyQR2 on the tensor cores -- two rounds of Gram matrix, Cholesky, triangular solve.  The
+ *     engine MEASURES ||Q1^T Q1 - I|| after the first round; a Cholesky breakdown (rank-deficient sketch) or a value above 0.05
+ *     (kappa(Y) beyond ~1e7) leaves the sketch untouched and the Householder TSQR runs instead, for that sketch and the rest of
+ *     the factorisation.  Same basis to working precision (orthogonality ~1e-15), ~4x faster on well-conditioned sketches.
+ *   policy 1: Householder TSQR always (also selected process-wide by the environment variable RSVDB_CHOLQR=0).
+ * rsvdb_qr_dev (the QR class) is always Householder: its R carries the reference's sign convention.
+ * rsvdb_qr_path_counts: sketches orthonormalised by either path since the context was created. */
+RSVDB_API int rsvdb_set_qr_policy(rsvdb_ctx* ctx, int policy);
+RSVDB_API int rsvdb_qr_path_counts(const rsvdb_ctx* ctx, int64_t* cholqr2, int64_t* householder);
 
 /* Optional per-phase device timing (CUDA events on the context's stream).  rsvdb_phase_ms synchronises the stream,
  * writes the accumulated milliseconds per phase since the last call and clears them.
@@ -97,6 +108,10 @@ RSVDB_API int rsvdb_gemm_at_dev(rsvdb_ctx* ctx, const double* dA, int64_t m, int
  * Identity(rows, l)` at src/rSVD.cpp:60-61,64-65,67-68.  dR (optional, l x l, leading dimension l) receives R.
  * sharded != 0: Y is this rank's row block and the R factors are combined across ranks. */
 RSVDB_API int rsvdb_qr_dev(rsvdb_ctx* ctx, double* dY, int64_t rows, int l, int64_t ldy, int sharded, double* dR);
+/* The same step as the rSVD pipeline itself runs it: Y <- an orthonormal basis of its columns under the context's QR policy
+ * (rsvdb_set_qr_policy: guarded CholeskyQR2, Householder TSQR when the guard refuses).  dR (optional, l x l, ld l): upper
+ * triangular with Y_in = Q R; its diagonal is positive when CholeskyQR2 ran.  *path (optional): 0 CholeskyQR2, 1 Householder. */
+RSVDB_API int rsvdb_orthonormalize_dev(rsvdb_ctx* ctx, double* dY, int64_t rows, int l, int64_t ldy, int sharded, double* dR, int* path);
 /* intermediate_step(A, Q, Omega, l, q) -- include/rSVD.hpp:13, src/rSVD.cpp:57-70.  A: this rank's m_local x n row block. */
 RSVDB_API int rsvdb_range_finder_dev(rsvdb_ctx* ctx, const double* dA, int64_t m_local, int64_t n, int64_t lda,
                                      const double* dOmega, int64_t ldo, int l, int q, double* dQ, int64_t ldq);

@@ -59,6 +59,8 @@ def _declare(lib):
         "rsvdb_launch_count": [vp],
         "rsvdb_generic_gemm_fallbacks": [],
         "rsvdb_split_gemm_products": [],
+        "rsvdb_set_qr_policy": [vp, c_int],
+        "rsvdb_qr_path_counts": [vp, POINTER(c_int64), POINTER(c_int64)],
         "rsvdb_set_profiling": [vp, c_int],
         "rsvdb_phase_ms": [vp, POINTER(c_double)],
         "rsvdb_last_svd_info": [vp, POINTER(c_int), POINTER(c_int)],
@@ -70,6 +72,7 @@ def _declare(lib):
         "rsvdb_gemm_an_dev": [vp, vp, i64, i64, i64, vp, i64, c_int, vp, i64],
         "rsvdb_gemm_at_dev": [vp, vp, i64, i64, i64, vp, i64, c_int, vp, i64, c_int],
         "rsvdb_qr_dev": [vp, vp, i64, c_int, i64, c_int, vp],
+        "rsvdb_orthonormalize_dev": [vp, vp, i64, c_int, i64, c_int, vp, POINTER(c_int)],
         "rsvdb_range_finder_dev": [vp, vp, i64, i64, i64, vp, i64, c_int, c_int, vp, i64],
         "rsvdb_rsvd_dev": [vp, vp, i64, i64, i64, vp, i64, c_int, c_int, c_int, u64, vp, i64, vp, vp, i64],
         "rsvdb_generate_omega_dev": [vp, i64, c_int, u64, vp, i64],

@@ -119,7 +119,8 @@ int rsvdb_destroy(rsvdb_ctx* c) {
   for (auto e : c->side_ev) if (e) cudaEventDestroy(e);
   for (auto& s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (auto e : c->event_pool) cudaEventDestroy(e);
-  c->gemm_ws.release(); c->qr_ws.release(); c->qr2_ws.release(); c->tmp_ws.release(); c->svd_ws.release(); c->io_ws.release(); c->wide_ws.release(); c->pca_ws.release(); c->pod_ws.release();
+  c->gemm_ws.release(); c->qr_ws.release(); c->qr2_ws.release(); c->tmp_ws.release(); c->svd_ws.release(); c->io_ws.release(); c->wide_ws.release(); c->pca_ws.release(); c->pod_ws.release(); c->chol_ws.release();
+  if (c->chol_host) cudaFreeHost(c->chol_host);
   delete c->stager;
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -145,6 +146,17 @@ const char* rsvdb_last_error(const rsvdb_ctx* c) { return c ? c->err.c_str() : "
 int64_t rsvdb_launch_count(const rsvdb_ctx* c) { return c ? c->launches : 0; }
 int64_t rsvdb_generic_gemm_fallbacks(void) { return generic_fallback_count(); }
 int64_t rsvdb_split_gemm_products(void) { return split_product_count(); }
+int rsvdb_set_qr_policy(rsvdb_ctx* c, int policy) {
+  if (!c || (policy != 0 && policy != 1)) return RSVDB_ERR_INVALID_ARGUMENT;
+  c->qr_policy = policy;
+  return RSVDB_OK;
+}
+int rsvdb_qr_path_counts(const rsvdb_ctx* c, int64_t* cholqr2, int64_t* householder) {
+  if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
+  if (cholqr2) *cholqr2 = c->qr_fast;
+  if (householder) *householder = c->qr_householder;
+  return RSVDB_OK;
+}
 
 int rsvdb_set_profiling(rsvdb_ctx* c, int enabled) {
   if (!c) return RSVDB_ERR_INVALID_ARGUMENT;
@@ -220,6 +232,18 @@ int rsvdb_qr_dev(rsvdb_ctx* c, double* dY, int64_t rows, int l, int64_t ldy, int
   const double* R = nullptr;
   RSVDB_TRY(qr_inplace(c, dY, rows, l, ldy, sharded != 0, &R));
   if (dR) RSVDB_CUDA(c, cudaMemcpyAsync(dR, R, (size_t)l * l * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return RSVDB_OK;
+}
+
+int rsvdb_orthonormalize_dev(rsvdb_ctx* c, double* dY, int64_t rows, int l, int64_t ldy, int sharded, double* dR, int* path) {
+  if (!c || rows < 0 || l <= 0 || ldy < rows) return fail(c, RSVDB_ERR_INVALID_ARGUMENT, "orthonormalize: bad shape");
+  RSVDB_CUDA(c, cudaSetDevice(c->device));
+  const double* R = nullptr;
+  const int64_t fast0 = c->qr_fast;
+  c->chol_failed = false;
+  RSVDB_TRY(orthonormalize(c, dY, rows, l, ldy, sharded != 0, &R));
+  if (dR) RSVDB_CUDA(c, cudaMemcpyAsync(dR, R, (size_t)l * l * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (path) *path = (c->qr_fast > fast0) ? 0 : 1;
   return RSVDB_OK;
 }
 

@@ -25,6 +25,12 @@ struct rsvdb_ctx {
   rsvdb::GemmWorkspace wide_ws;     // wide-panel QR (l > 100): R, projection coefficients, product buffer
   rsvdb::GemmWorkspace pca_ws;      // column statistics, implicit-centring operands
   rsvdb::GemmWorkspace pod_ws;      // POD: correlation matrix, SVD factors of it
+  rsvdb::GemmWorkspace chol_ws;     // CholeskyQR2 fast path: the intermediate panel, Gram matrices, triangular factors
+  double* chol_host = nullptr;      // pinned: the guard's verdict (pivot breakdown, ||Q1^T Q1 - I||_F^2)
+  int qr_policy = -1;               // -1: environment default (RSVDB_CHOLQR), 0: guarded CholeskyQR2 then Householder, 1: Householder only
+  bool chol_failed = false;         // the guard refused a sketch of the factorisation in flight: stay on Householder for the rest of it
+  bool in_rsvd = false;
+  int64_t qr_fast = 0, qr_householder = 0;   // sketches orthonormalised by either path (rsvdb_qr_path_counts)
   int64_t launches = 0;
   std::string err;
   // multi-GPU (row-sharded A); comm is an ncclComm_t resolved at run time (comm.cu)

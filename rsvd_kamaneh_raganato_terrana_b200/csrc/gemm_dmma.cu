@@ -372,20 +372,47 @@ k_gemm_at(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 // Sum nsplit partial (rows x cols) tiles in a fixed order.  Partials are column-major with leading dimension ld_ws.
 // transpose == 0: out[r + c*ld_out]; transpose == 1: out[c + r*ld_out] (staged through shared memory so both sides coalesce).
+// gridDim.z > 1: slab z sums the partials [z * group, min(nsplit, (z + 1) * group)) into out + z * out_z_stride (first stage of
+// the two-stage reduction used when the output has too few tiles to occupy the GPU).
 __global__ void k_reduce_splits(const double* __restrict__ ws, long long split_stride, int nsplit, long long ld_ws,
-                                double* __restrict__ out, long long ld_out, int rows, int cols, int transpose) {
+                                double* __restrict__ out, long long ld_out, int rows, int cols, int transpose,
+                                int group, long long out_z_stride) {
   __shared__ double tile[32][33];
+  if (gridDim.z > 1) {
+    const int k0 = blockIdx.z * group;
+    ws += (size_t)k0 * split_stride; out += (size_t)blockIdx.z * out_z_stride;
+    nsplit = min(group, nsplit - k0);
+  }
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
-  for (int cc = ty; cc < 32; cc += 8) {
-    const int r = r0 + tx, c = c0 + cc;
-    double s = 0.0;
-    if (r < rows && c < cols) {
-      const double* src = ws + (size_t)c * ld_ws + r;
-      for (int k = 0; k < nsplit; ++k) s += src[(size_t)k * split_stride];
-      if (!transpose) out[(size_t)c * ld_out + r] = s;
-    }
-    tile[cc][tx] = s;
+  // the four elements of a thread and eight partials of each are loaded together (32 independent loads in flight: with few
+  // output tiles -- a Gram matrix -- the kernel is latency-bound); the additions keep the fixed order k = 0, 1, 2, ...
+  const int r = r0 + tx;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  bool on[4];
+  const double* src[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c = c0 + ty + 8 * q;
+    on[q] = r < rows && c < cols;
+    src[q] = ws + (size_t)(on[q] ? c : 0) * ld_ws + (on[q] ? r : 0);
+  }
+  for (int k = 0; k < nsplit; k += 8) {
+    double v[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[q][u] = (on[q] && k + u < nsplit) ? src[q][(size_t)(k + u) * split_stride] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (k + u < nsplit) s[q] += v[q][u];
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int cc = ty + 8 * q, c = c0 + cc;
+    if (on[q] && !transpose) out[(size_t)c * ld_out + r] = s[q];
+    tile[cc][tx] = s[q];
   }
   if (transpose) {
     __syncthreads();
@@ -485,7 +512,8 @@ void choose_split(int ntiles, int ksteps, int nsm, long long out_elems, int nb, 
   const double kstep_us = (double)BM * (8.0 * nb) * BK * 2.0 / (37.1e12 / nsm) * 1e6;   // one CTA, one slab, at the DMMA rate
   const double reduce_units = ((double)out_elems * 8.0 / 6.5e12 * 1e6) / kstep_us;
   int best = 1; double best_t = 1e300;
-  const int smax = std::max(1, std::min(48, ksteps / 8));
+  // at most 48 slabs, except when the output has so few tiles (a Gram matrix: one) that 48 would leave SMs idle
+  const int smax = std::max(1, std::min(std::max(48, nsm / std::max(1, ntiles)), ksteps / 8));
   for (int s = 1; s <= smax; ++s) {
     const long long units = (long long)ntiles * s;
     const long long waves = (units + nsm - 1) / nsm;
@@ -562,6 +590,32 @@ __global__ void k_repack(const double* __restrict__ src, long long lds, double* 
   if (i < rows) for (int k = blockIdx.y; k < cols; k += gridDim.y) dst[(size_t)k * ldd + i] = src[(size_t)k * lds + i];
 }
 
+// Fixed-order sum of the split-K partials.  An output of a few tiles (a Gram matrix: 16) with many slabs would leave one thread
+// chasing ~150 dependent loads on 16 SMs; it is reduced in two stages instead (groups of ~sqrt(nsplit) slabs over gridDim.z, then
+// the group sums): same result on every run and every rank, ~4x shorter.  `scratch` holds reduce_groups() partial outputs.
+int reduce_groups(long long rows, int cols, int nsplit) {
+  const long long tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+  if (tiles > 64 || nsplit < 24) return 1;
+  int nz = 1; while (nz * nz < nsplit) ++nz;
+  return nz;
+}
+cudaError_t reduce_partials(cudaStream_t st, const double* part, long long split_stride, int nsplit, long long ld_ws, double* out,
+                            long long ld_out, int rows, int cols, int transpose, double* scratch, int* launches) {
+  dim3 rg((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  const int nz = reduce_groups(rows, cols, nsplit);
+  if (nz > 1) {
+    const int group = (nsplit + nz - 1) / nz, nzz = (nsplit + group - 1) / group;
+    const long long zs = (long long)rows * cols;
+    k_reduce_splits<<<dim3(rg.x, rg.y, (unsigned)nzz), dim3(32, 8), 0, st>>>(part, split_stride, nsplit, ld_ws, scratch, rows, rows, cols, 0, group, zs);
+    k_reduce_splits<<<rg, dim3(32, 8), 0, st>>>(scratch, zs, nzz, rows, out, ld_out, rows, cols, transpose, 0, 0);
+    if (launches) *launches += 2;
+  } else {
+    k_reduce_splits<<<rg, dim3(32, 8), 0, st>>>(part, split_stride, nsplit, ld_ws, out, ld_out, rows, cols, transpose, 0, 0);
+    if (launches) ++*launches;
+  }
+  return cudaGetLastError();
+}
+
 static long long g_generic_fallbacks = 0;   // products that took the CUDA-core kernel (operands TMA cannot describe at all)
 static long long g_split_products = 0;      // products whose A needed the two-map (odd lda / 8-byte aligned base) path
 void note_generic_fallback() { ++g_generic_fallbacks; }
@@ -602,7 +656,11 @@ cudaError_t gemm_an(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
   int nsplit, kchunk; choose_split(ntiles, ksteps, nsm, M * std::min(N, 128), (std::min(N, 128) + 7) / 8, &nsplit, &kchunk);
   const long long ldw = (M + 1) & ~1LL, ldxr = (K + 1) & ~1LL;
   const size_t part_bytes = nsplit > 1 ? (((size_t)nsplit * ldw * std::min(N, 128) * 8 + 255) & ~size_t(255)) : 0;
-  if (part_bytes || repackX) { cudaError_t e = ws.reserve(part_bytes + (repackX ? (size_t)ldxr * N * 8 : 0)); if (e != cudaSuccess) return e; }
+  const size_t repack_bytes = repackX ? (((size_t)ldxr * N * 8 + 255) & ~size_t(255)) : 0;
+  const int rgroups = nsplit > 1 ? reduce_groups(M, std::min(N, 128), nsplit) : 1;
+  const size_t scratch_bytes = rgroups > 1 ? (size_t)(rgroups + 1) * M * std::min(N, 128) * 8 : 0;
+  if (part_bytes || repackX) { cudaError_t e = ws.reserve(part_bytes + repack_bytes + scratch_bytes); if (e != cudaSuccess) return e; }
+  double* scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(ws.ptr) + part_bytes + repack_bytes);
   if (repackX) {
     double* Xr = reinterpret_cast<double*>(reinterpret_cast<char*>(ws.ptr) + part_bytes);
     k_repack<<<dim3((unsigned)((K + 255) / 256), (unsigned)std::min(N, 128)), 256, 0, st>>>(X, ldx, Xr, ldxr, K, N);
@@ -629,10 +687,8 @@ cudaError_t gemm_an(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
     if (nsplit > 1) {
-      dim3 rg((unsigned)((M + 31) / 32), (unsigned)((nc + 31) / 32));
-      k_reduce_splits<<<rg, dim3(32, 8), 0, st>>>(ws.ptr, p.split_stride, nsplit, p.ld_out, yout, ldy, (int)M, nc, 0);
-      e = cudaGetLastError(); if (e != cudaSuccess) return e;
-      if (launches) ++*launches;
+      e = reduce_partials(st, ws.ptr, p.split_stride, nsplit, p.ld_out, yout, ldy, (int)M, nc, 0, scratch, launches);
+      if (e != cudaSuccess) return e;
     }
   }
   return cudaSuccess;
@@ -662,7 +718,11 @@ cudaError_t gemm_at(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
   int nsplit, kchunk; choose_split(ntiles, ksteps, nsm, M * std::min(N, 128), (std::min(N, 128) + 7) / 8, &nsplit, &kchunk);
   const long long ldqr = (K + 1) & ~1LL;
   const size_t part_bytes = nsplit > 1 ? (((size_t)nsplit * M * std::min(N, 128) * 8 + 255) & ~size_t(255)) : 0;
-  if (part_bytes || repackQ) { cudaError_t e = ws.reserve(part_bytes + (repackQ ? (size_t)ldqr * N * 8 : 0)); if (e != cudaSuccess) return e; }
+  const size_t repack_bytes = repackQ ? (((size_t)ldqr * N * 8 + 255) & ~size_t(255)) : 0;
+  const int rgroups = nsplit > 1 ? reduce_groups(M, std::min(N, 128), nsplit) : 1;
+  const size_t scratch_bytes = rgroups > 1 ? (size_t)(rgroups + 1) * M * std::min(N, 128) * 8 : 0;
+  if (part_bytes || repackQ) { cudaError_t e = ws.reserve(part_bytes + repack_bytes + scratch_bytes); if (e != cudaSuccess) return e; }
+  double* scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(ws.ptr) + part_bytes + repack_bytes);
   if (repackQ) {
     double* Qr = reinterpret_cast<double*>(reinterpret_cast<char*>(ws.ptr) + part_bytes);
     k_repack<<<dim3((unsigned)((K + 255) / 256), (unsigned)std::min(N, 128)), 256, 0, st>>>(Q, ldq, Qr, ldqr, K, N);
@@ -688,10 +748,8 @@ cudaError_t gemm_at(GemmWorkspace& ws, cudaStream_t st, int nsm, const double* A
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
     if (nsplit > 1) {
-      dim3 rg((unsigned)((M + 31) / 32), (unsigned)((nc + 31) / 32));
-      k_reduce_splits<<<rg, dim3(32, 8), 0, st>>>(ws.ptr, p.split_stride, nsplit, p.ld_out, zout, ldz, (int)M, nc, transpose_out);
-      e = cudaGetLastError(); if (e != cudaSuccess) return e;
-      if (launches) ++*launches;
+      e = reduce_partials(st, ws.ptr, p.split_stride, nsplit, p.ld_out, zout, ldz, (int)M, nc, transpose_out, scratch, launches);
+      if (e != cudaSuccess) return e;
     }
   }
   return cudaSuccess;

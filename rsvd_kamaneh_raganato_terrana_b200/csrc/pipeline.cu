@@ -263,6 +263,7 @@ static int upload_and_first_pass(rsvdb_ctx* c, double* A, int64_t m, int64_t n, 
 int range_finder(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda, const double* Omega, int64_t ldo,
                  int l, int q, double* Q, int64_t ldq, const HostUpload* up, const Centering* cen) {
   if (l <= 0 || q < 0) return fail(c, -1, "range_finder: l must be positive and q non-negative");
+  c->chol_failed = false;                          // a new factorisation: the fast orthonormalisation gets its chance again
   // Z (n x l, even leading dimension: TMA needs 16-byte column strides) lives in tmp_ws at offset 0
   const int64_t ldz = even_ld(n);
   RSVDB_CUDA(c, c->tmp_ws.reserve(std::max<size_t>(c->tmp_ws.bytes, (size_t)ldz * l * sizeof(double))));
@@ -275,12 +276,12 @@ int range_finder(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t ld
   } else {
     RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Omega, ldo, l, Q, ldq, cen));     // Y = A * Omega          src/rSVD.cpp:59
   }
-  RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));                       // Q = qr(Y).Q            :60-61
+  RSVDB_TRY(orthonormalize(c, Q, m, l, ldq, true, nullptr));                   // Q = qr(Y).Q            :60-61
   for (int it = 0; it < q; ++it) {                                             // :62
     RSVDB_TRY(gemm_at_phase(c, A, m, n, lda, Q, ldq, l, Z, ldz, 0, true, cen));// Y = A^T * Q            :63
-    RSVDB_TRY(qr_inplace(c, Z, n, l, ldz, false, nullptr));                    // Q = qr(Y).Q  (n x l)   :64-65
+    RSVDB_TRY(orthonormalize(c, Z, n, l, ldz, false, nullptr));                // Q = qr(Y).Q  (n x l)   :64-65
     RSVDB_TRY(gemm_an_phase(c, A, m, n, lda, Z, ldz, l, Q, ldq, cen));         // Y = A * Q              :66
-    RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));                     // Q = qr(Y).Q            :67-68
+    RSVDB_TRY(orthonormalize(c, Q, m, l, ldq, true, nullptr));                 // Q = qr(Y).Q            :67-68
   }
   return 0;
 }
@@ -288,6 +289,7 @@ int range_finder(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t ld
 int small_svd_jacobi(rsvdb_ctx* c, const double* M, int64_t ldm, const double* Mt, int64_t ldmt, int64_t r, int64_t cd,
                      double* U, int64_t ldu, double* S, double* V, int64_t ldv) {
   PhaseTimer pt(c, PH_SMALL_SVD);
+  if (!c->in_rsvd) c->chol_failed = false;         // a stand-alone SVD<Jacobi>: its own factorisation
   const int64_t k = std::min(r, cd);
   if (k <= 0) return 0;
   if (k > 32768) return fail(c, -6, "SVD<Jacobi>: min(rows, cols) > 32768 is not supported (two k x k work matrices must fit in device memory)");
@@ -308,7 +310,7 @@ int small_svd_jacobi(rsvdb_ctx* c, const double* M, int64_t ldm, const double* M
     if (M) { RSVDB_TRY(copy2d(c, M, ldm, T, r, r, (int)cd)); }
     else { RSVDB_TRY(transpose2d(c, Mt, ldmt, T, r, cd, r)); }
     const double* R = nullptr;
-    RSVDB_TRY(qr_inplace(c, T, r, (int)cd, r, false, &R));
+    RSVDB_TRY(orthonormalize(c, T, r, (int)cd, r, false, &R));
     RSVDB_CUDA(c, jacobi_svd_square(jws, c->stream, R, cd, (int)k, 0, Uw, k, S, V, ldv, info, &nl));
     RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, T, r, k, r, Uw, k, (int)k, U, ldu, &nl));
   } else {
@@ -316,7 +318,7 @@ int small_svd_jacobi(rsvdb_ctx* c, const double* M, int64_t ldm, const double* M
     if (Mt) { RSVDB_TRY(copy2d(c, Mt, ldmt, T, cd, cd, (int)r)); }
     else { RSVDB_TRY(transpose2d(c, M, ldm, T, cd, r, cd)); }
     const double* R = nullptr;
-    RSVDB_TRY(qr_inplace(c, T, cd, (int)r, cd, false, &R));
+    RSVDB_TRY(orthonormalize(c, T, cd, (int)r, cd, false, &R));
     RSVDB_CUDA(c, jacobi_svd_square(jws, c->stream, R, r, (int)k, 1, U, ldu, S, Zw, k, info, &nl));
     RSVDB_CUDA(c, gemm_an(c->gemm_ws, c->stream, c->nsm, T, cd, k, cd, Zw, k, (int)k, V, ldv, &nl));
   }
@@ -331,6 +333,7 @@ int rsvd_device(rsvdb_ctx* c, const double* A, int64_t m, int64_t n, int64_t lda
   if (method != 0 && method != 1 && method != 2) return fail(c, -1, "Unsupported SVD method");   // src/rSVD.cpp:122-123
   if (l <= 0 || n <= 0 || m < 0) return fail(c, -1, "rSVD: bad shape");
   const int64_t k = std::min<int64_t>(l, n);
+  struct InRsvd { rsvdb_ctx* c; InRsvd(rsvdb_ctx* x) : c(x) { c->in_rsvd = true; } ~InRsvd() { c->in_rsvd = false; } } in_rsvd(c);
   // tmp_ws layout: [Z / Bt : n x l][Q : m x l][Ut : l x k]; even leading dimensions and even offsets keep every
   // sub-buffer TMA-addressable (16-byte base and column stride) whatever the parity of m, n and l
   const int64_t ldz = even_ld(n), ldq = even_ld(m), ldut = even_ld(l);

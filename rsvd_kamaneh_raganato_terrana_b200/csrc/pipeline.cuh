@@ -14,6 +14,11 @@ inline int64_t even_ld(int64_t rows) { return rows < 2 ? 2 : ((rows + 1) & ~int6
 // (leading dimension l), valid until the next QR on this context.
 int qr_inplace(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bool sharded, const double** R);
 
+// Orthonormal basis of the columns of Y in place, as the pipeline needs it (cholqr.cu): guarded CholeskyQR2 when the sketch is
+// numerically full-rank and well enough conditioned (decided from the measured ||Q1^T Q1 - I||), else qr_inplace.  *R (optional):
+// l x l upper triangular with Y_in = Q R (its diagonal is positive on the fast path, Householder-signed otherwise).
+int orthonormalize(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bool sharded, const double** R);
+
 // A still lives in host memory when the path starts (the host-pointer entry points): the upload is cut into row blocks
 // on the side stream and the first product Y = A * Omega consumes each block as it lands, so all but the last block's
 // share of that pass hides under the PCIe transfer.

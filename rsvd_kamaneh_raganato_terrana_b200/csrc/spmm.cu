@@ -197,12 +197,13 @@ int rsvd_csr_device(rsvdb_ctx* c, int64_t m, int64_t n, int64_t nnz, const int64
     return 0;
   };
   RSVDB_TRY(spmm_a(Omega, ldo, Q, ldq));                              // Y = A * Omega                  src/rSVD.cpp:59
-  RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));              // :60-61
+  c->chol_failed = false;
+  RSVDB_TRY(orthonormalize(c, Q, m, l, ldq, true, nullptr));          // :60-61
   for (int it = 0; it < q; ++it) {
     RSVDB_TRY(spmm_at(Q, ldq, Bt, ldb));                              // Y = A^T * Q                    :63
-    RSVDB_TRY(qr_inplace(c, Bt, n, l, ldb, false, nullptr));          // :64-65
+    RSVDB_TRY(orthonormalize(c, Bt, n, l, ldb, false, nullptr));      // :64-65
     RSVDB_TRY(spmm_a(Bt, ldb, Q, ldq));                               // Y = A * Q                      :66
-    RSVDB_TRY(qr_inplace(c, Q, m, l, ldq, true, nullptr));            // :67-68
+    RSVDB_TRY(orthonormalize(c, Q, m, l, ldq, true, nullptr));        // :67-68
   }
   RSVDB_TRY(spmm_at(Q, ldq, Bt, ldb));                                // B^T = A^T Q                    :89
   if (method == 1) { RSVDB_TRY(small_svd_power_t(c, Bt, ldb, l, n, 0, seed, Ut, ldut, l, S, V, ldv, nullptr)); }

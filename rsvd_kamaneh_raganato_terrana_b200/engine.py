@@ -83,6 +83,16 @@ class Engine:
     def launches(self) -> int:
         return int(self.lib.rsvdb_launch_count(self.h))
 
+    def set_qr_policy(self, householder_only: bool):
+        """False (default): guarded CholeskyQR2 with Householder TSQR as the fallback; True: Householder TSQR always."""
+        self._check(self.lib.rsvdb_set_qr_policy(self.h, 1 if householder_only else 0))
+
+    def qr_path_counts(self):
+        """(sketches orthonormalised by CholeskyQR2, by Householder TSQR) since the engine was created."""
+        a = ctypes.c_int64(); b = ctypes.c_int64()
+        self._check(self.lib.rsvdb_qr_path_counts(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def set_profiling(self, on: bool):
         self._check(self.lib.rsvdb_set_profiling(self.h, int(on)))
 
@@ -117,6 +127,12 @@ class Engine:
 
     def qr_dev(self, dY, rows, l, ldy, sharded=False, dR=None):
         self._check(self.lib.rsvdb_qr_dev(self.h, dY, rows, l, ldy, int(sharded), dR))
+
+    def orthonormalize_dev(self, dY, rows, l, ldy, sharded=False, dR=None) -> int:
+        """Y <- orthonormal basis of its columns as the rSVD pipeline computes it; returns 0 (CholeskyQR2) or 1 (Householder)."""
+        path = ctypes.c_int(-1)
+        self._check(self.lib.rsvdb_orthonormalize_dev(self.h, dY, rows, l, ldy, int(sharded), dR, ctypes.byref(path)))
+        return path.value
 
     def range_finder_dev(self, dA, m_local, n, lda, dOmega, ldo, l, q, dQ, ldq):
         self._check(self.lib.rsvdb_range_finder_dev(self.h, dA, m_local, n, lda, dOmega, ldo, l, q, dQ, ldq))
