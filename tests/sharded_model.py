@@ -22,6 +22,69 @@ def tsqr_sharded(Y_p, dist, torch, O):
     return Q1 @ Q2[p * l:(p + 1) * l, :], R
 
 
+CHOL_DEV_TOL = 0.05
+
+
+def _chol_inv(G):
+    """cholqr.cu k_chol_inv: (breakdown, ||G - I||_F^2, X = R^-1, R) of G = R^T R; breakdown = first non-positive pivot."""
+    l = G.shape[0]
+    dev2 = float(np.sum((np.tril(G) - np.eye(l)) ** 2) + np.sum(np.tril(G, -1) ** 2))
+    Lw = np.tril(G).copy(); Wi = np.eye(l)
+    for j in range(l):
+        d = Lw[j, j]
+        if not (d > 0.0) or not np.isfinite(d):
+            return j + 1, dev2, None, None
+        s = 1.0 / np.sqrt(d)
+        Lw[j:, j] *= s; Wi[j, :j + 1] *= s
+        for i in range(j + 1, l):
+            Lw[i, j + 1:i + 1] -= Lw[i, j] * Lw[j + 1:i + 1, j]
+            Wi[i, :j + 1] -= Lw[i, j] * Wi[j, :j + 1]
+    return 0, dev2, Wi.T, Lw.T
+
+
+def orthonormalize_sharded(Y_p, dist, torch, O, state):
+    """cholqr.cu orthonormalize on a row-sharded sketch: Gram matrices are all-reduced (every rank factors the same bits and takes
+    the same decision), the guard reads the SECOND Gram matrix before Y is overwritten, the TSQR is the fallback."""
+    if not state.get("failed", False):
+        bad1, _, X1, R1 = _chol_inv(_allreduce(Y_p.T @ Y_p, dist, torch))
+        if not bad1:
+            T_p = Y_p @ X1
+            bad2, dev2, X2, R2 = _chol_inv(_allreduce(T_p.T @ T_p, dist, torch))
+            if not bad2 and dev2 <= CHOL_DEV_TOL ** 2:
+                state["fast"] = state.get("fast", 0) + 1
+                return T_p @ X2, R2 @ R1
+        state["failed"] = True
+    state["householder"] = state.get("householder", 0) + 1
+    return tsqr_sharded(Y_p, dist, torch, O)
+
+
+def orthonormalize_replicated(Z, O, state):
+    if not state.get("failed", False):
+        bad1, _, X1, R1 = _chol_inv(Z.T @ Z)
+        if not bad1:
+            T = Z @ X1
+            bad2, dev2, X2, R2 = _chol_inv(T.T @ T)
+            if not bad2 and dev2 <= CHOL_DEV_TOL ** 2:
+                state["fast"] = state.get("fast", 0) + 1
+                return T @ X2, R2 @ R1
+        state["failed"] = True
+    state["householder"] = state.get("householder", 0) + 1
+    return O.householder_qr(Z)
+
+
+def rsvd_sharded_guarded(A_p, Omega, l, q, dist, torch, O, state):
+    """rsvd_sharded with the orthonormalisations the product runs by default (guarded CholeskyQR2, Householder fallback)."""
+    state.clear()
+    Q_p, _ = orthonormalize_sharded(A_p @ Omega, dist, torch, O, state)
+    for _ in range(q):
+        Qz, _ = orthonormalize_replicated(_allreduce(A_p.T @ Q_p, dist, torch), O, state)
+        Q_p, _ = orthonormalize_sharded(A_p @ Qz, dist, torch, O, state)
+    Bt = _allreduce(A_p.T @ Q_p, dist, torch)
+    Qb, Rb = orthonormalize_replicated(Bt, O, state)                    # include/SVD_class.hpp:116-123: QR of B^T, Jacobi on R^T
+    Ur, S, Vr, _ = O.svd_jacobi(Rb.T)
+    return Q_p @ Ur, S, Qb @ Vr
+
+
 def rsvd_sharded(A_p, Omega, l, q, dist, torch, O):
     Q_p, _ = tsqr_sharded(A_p @ Omega, dist, torch, O)                 # shard-local product, distributed QR
     for _ in range(q):

@@ -1462,3 +1462,103 @@ def test_rsvd_csr_shape_sweep(engine, oracle, m, n, l, q):
     Uo, So, Vo = oracle.rsvd(Ad, Om, l, q, oracle.JACOBI)
     assert oracle.sigma_close(Sg, So)[0]
     assert abs(oracle.reconstruction_error(Ad, Ug, Sg, Vg) - oracle.reconstruction_error(Ad, Uo, So, Vo)) <= 1e-8 * np.linalg.norm(Ad)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the pipeline's orthonormalisation: guarded CholeskyQR2 with the Householder TSQR as fallback (csrc/cholqr.cu) --
+# replaces HouseholderQR + thin Q at src/rSVD.cpp:60-68 and the QR preconditioner of include/SVD_class.hpp:110-123
+# ---------------------------------------------------------------------------------------------------------------------
+def _sketch(torch, dev, rows, l, kind, seed=0):
+    g = torch.Generator(device=dev); g.manual_seed(seed + 977 * rows + l)
+    Y = torch.randn((l, rows), dtype=torch.float64, device=dev, generator=g)              # column-major rows x l
+    if kind == "rank5":
+        Y[5:] = torch.randn((l - 5, 5), dtype=torch.float64, device=dev, generator=g) @ Y[:5]
+    elif kind == "zero_col":
+        Y[l // 2] = 0.0
+    elif kind.startswith("kappa"):
+        Q, _ = torch.linalg.qr(Y.T)
+        Wm, _ = torch.linalg.qr(torch.randn((l, l), dtype=torch.float64, device=dev, generator=g))
+        s = 10.0 ** (-float(kind[5:]) * torch.arange(l, dtype=torch.float64, device=dev) / (l - 1))
+        Y = ((Q * s) @ Wm.T).T.contiguous()
+    return Y
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("rows,l,kind,path", [
+    (20000, 100, "randn", 0), (25001, 100, "randn", 0), (4096, 50, "randn", 0), (3000, 97, "randn", 0), (9999, 128, "randn", 0),
+    (12345, 37, "kappa3", 0), (20000, 100, "kappa6", 0),                        # well inside the guard
+    (20000, 100, "kappa10", 1), (20000, 64, "kappa14", 1),                      # the measured ||Q1^T Q1 - I|| refuses them
+    (5000, 50, "rank5", 1), (3000, 64, "zero_col", 1), (2049, 100, "rank5", 1), # Cholesky breakdown
+    (30000, 8, "randn", 1), (300, 100, "randn", 1), (30000, 129, "randn", 1),   # outside the fast path's range by construction
+])
+def test_orthonormalize_guarded_cholqr2_and_householder_fallback(engine, rows, l, kind, path):
+    import torch
+    dev = torch.device("cuda:0")
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        Y0 = _sketch(torch, dev, rows, l, kind); Y = Y0.clone()
+        R = torch.zeros((l, l), dtype=torch.float64, device=dev)
+        f0, h0 = engine.qr_path_counts()
+        took = engine.orthonormalize_dev(Y.data_ptr(), rows, l, rows, False, R.data_ptr()); torch.cuda.synchronize()
+        f1, h1 = engine.qr_path_counts()
+        assert took == path and (f1 - f0, h1 - h0) == ((1, 0) if path == 0 else (0, 1))
+        Q, Rm = Y.T, R.T
+        eye = torch.eye(l, dtype=torch.float64, device=dev)
+        assert (Q.T @ Q - eye).norm().item() <= 1e-12                                     # tolerance: 1e-10 (ORTH_TOL) with margin
+        assert ((Q @ Rm - Y0.T).norm() / Y0.norm()).item() <= 1e-13
+        assert torch.tril(Rm, -1).abs().max().item() == 0.0
+        if path == 0:
+            assert bool((torch.diagonal(Rm) > 0).all().item())
+        # same basis as the Householder-only policy: the projector onto the numerically non-degenerate part agrees
+        engine.set_qr_policy(True)
+        Yh = Y0.clone()
+        assert engine.orthonormalize_dev(Yh.data_ptr(), rows, l, rows, False, None) == 1; torch.cuda.synchronize()
+        if kind in ("randn", "kappa3", "kappa6"):
+            Qh = Yh.T
+            assert (Q - Qh @ (Qh.T @ Q)).norm().item() <= 1e-9 * (10.0 ** (6 if kind == "kappa6" else 0))
+    finally:
+        engine.set_qr_policy(False)
+        engine.lib.rsvdb_use_own_stream(engine.h)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("m,n,l,q", [(20000, 3000, 100, 2), (5000, 4000, 64, 1), (3001, 2001, 33, 3)])
+def test_rsvd_is_the_same_under_both_qr_policies(engine, oracle, m, n, l, q):
+    rng = np.random.default_rng(m + n)
+    A = np.asfortranarray((rng.standard_normal((m, 40)) * (0.8 ** np.arange(40))) @ rng.standard_normal((40, n)) + 1e-3 * rng.standard_normal((m, n)))
+    Om = W.omega(n, l)
+    try:
+        f0, h0 = engine.qr_path_counts()
+        U1, S1, V1 = engine.rSVD(A, l, SVDMethod.Jacobi, Omega=Om, q=q)
+        f1, h1 = engine.qr_path_counts()
+        assert f1 - f0 == 2 * q + 2 and h1 == h0                                          # 2q + 1 sketches + the preconditioner
+        engine.set_qr_policy(True)
+        U2, S2, V2 = engine.rSVD(A, l, SVDMethod.Jacobi, Omega=Om, q=q)
+        f2, h2 = engine.qr_path_counts()
+        assert f2 == f1 and h2 - h1 == 2 * q + 2
+    finally:
+        engine.set_qr_policy(False)
+    assert np.max(np.abs(S1 - S2)) <= 1e-12 * S2[0]
+    Uo, So, Vo = oracle.rsvd(A, Om, l, q, oracle.JACOBI)
+    check_rsvd(oracle, A, U1, S1, V1, Uo, So, Vo, l)
+    check_rsvd(oracle, A, U2, S2, V2, Uo, So, Vo, l)
+
+
+def test_rank_deficient_sketches_leave_the_fast_path_for_the_whole_factorisation(engine, oracle):
+    """Reference config 1 in spirit: a rank-2 matrix sketched with l = 16.  The first Cholesky breaks down, the sketch is
+    untouched, and every orthonormalisation of this rSVD runs on the Householder TSQR (one wasted attempt, not 2q + 2)."""
+    m, n, l, q = 4000, 600, 16, 2
+    rng = np.random.default_rng(5)
+    A = np.asfortranarray(rng.standard_normal((m, 2)) @ rng.standard_normal((2, n)))
+    Om = W.omega(n, l)
+    f0, h0 = engine.qr_path_counts()
+    U, S, V = engine.rSVD(A, l, SVDMethod.Jacobi, Omega=Om, q=q)
+    f1, h1 = engine.qr_path_counts()
+    assert f1 == f0 and h1 - h0 == 2 * q + 2
+    Uo, So, Vo = oracle.rsvd(A, Om, l, q, oracle.JACOBI)
+    check_rsvd(oracle, A, U, S, V, Uo, So, Vo, l)
+    # the next factorisation gets its chance again
+    B = np.asfortranarray(rng.standard_normal((m, n)))
+    engine.rSVD(B, l, SVDMethod.Jacobi, Omega=Om, q=1)
+    f2, h2 = engine.qr_path_counts()
+    assert f2 - f1 == 4 and h2 == h1

@@ -98,6 +98,54 @@ def test_sharded_rsvd_two_gloo_ranks(tmp_path, oracle):
     assert oracle.subspace_sin_theta(Uo, U) < 1e-8
 
 
+def _guarded_worker(rank, world, port, m, n, l, q, rank_def, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle import rsvd_oracle as O
+    import sharded_model
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    A = _guarded_case(m, n, rank_def)
+    Om = W.omega(n, l)
+    off, rows = W.row_split(m, world, rank)
+    state = {}
+    U_p, S, V = sharded_model.rsvd_sharded_guarded(A[off:off + rows], Om, l, q, dist, torch, O, state)
+    np.savez(Path(out_dir) / f"r{rank}.npz", U=U_p, S=S, V=V, off=off, fast=state.get("fast", 0), householder=state.get("householder", 0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _guarded_case(m, n, rank_def):
+    rng = np.random.default_rng(7)
+    if rank_def:
+        return rng.standard_normal((m, 3)) @ rng.standard_normal((3, n))
+    return rng.standard_normal((m, 40)) @ np.diag(0.8 ** np.arange(40)) @ rng.standard_normal((40, n)) + 1e-3 * rng.standard_normal((m, n))
+
+
+@pytest.mark.parametrize("rank_def", [False, True])
+def test_sharded_guarded_cholqr2_two_gloo_ranks(tmp_path, oracle, rank_def):
+    """cholqr.cu over row shards, restated with numpy + gloo: all-reduced Gram matrices, identical guard decisions on every rank
+    (a rank-deficient matrix sends BOTH ranks to the TSQR at the first sketch and keeps them there), same factorisation as the oracle."""
+    import torch.multiprocessing as mp
+    m, n, l, q, world = 301, 120, 12, 2, 2
+    port = _free_port()
+    mp.spawn(_guarded_worker, args=(world, port, m, n, l, q, rank_def, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    U = np.vstack([p["U"] for p in parts]); S = parts[0]["S"]; V = parts[0]["V"]
+    assert np.array_equal(parts[0]["S"], parts[1]["S"]) and np.array_equal(parts[0]["V"], parts[1]["V"])   # replicated, bit-identical
+    counts = [(int(p["fast"]), int(p["householder"])) for p in parts]
+    assert counts[0] == counts[1] == ((0, 2 * q + 2) if rank_def else (2 * q + 2, 0))
+    A = _guarded_case(m, n, rank_def)
+    Uo, So, Vo = oracle.rsvd(A, W.omega(n, l), l, q, oracle.JACOBI)
+    assert np.all(np.abs(S - So) <= 1e-10 * So[0])
+    r = 3 if rank_def else l
+    assert np.linalg.norm(U.T @ U - np.eye(l)) < 1e-12
+    assert abs(oracle.reconstruction_error(A, U, S, V) - oracle.reconstruction_error(A, Uo, So, Vo)) < 1e-9 * np.linalg.norm(A)
+    assert oracle.subspace_sin_theta(Uo[:, :r], U[:, :r]) < 1e-8
+
+
 def _rpca_worker(rank, world, port, m, n, l, q, out_dir):
     import torch
     import torch.distributed as dist

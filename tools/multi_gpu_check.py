@@ -35,6 +35,11 @@ for (m, n, l, q, gen) in [(3001, 400, 32, 2, "pod"), (20000, 1500, 100, 2, "gaus
     Sall = [torch.empty(len(S), dtype=torch.float64, device=dev) for _ in range(world)]
     dist.all_gather(Sall, torch.from_numpy(S).to(dev))
     same_S = all(torch.equal(Sall[0], s) for s in Sall)
+    # the guard of the CholeskyQR2 fast path must send every rank down the same branch (its collectives differ from the TSQR's)
+    cnt = torch.tensor(E.qr_path_counts(), dtype=torch.int64, device=dev)
+    call = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(call, cnt)
+    same_S = same_S and all(torch.equal(call[0], x) for x in call)
     if rank == 0:
         Uo, So, Vo = O.rsvd(A, Om, l, q, O.JACOBI)
         okS, relS = O.sigma_close(S, So)
@@ -42,7 +47,8 @@ for (m, n, l, q, gen) in [(3001, 400, 32, 2, "pod"), (20000, 1500, 100, 2, "gaus
         orthU = np.linalg.norm(U.T @ U - np.eye(U.shape[1]))
         ok = okS and eg <= eo + 1e-8 * np.linalg.norm(A) and orthU < 1e-10 and same_S
         ok_all &= ok
-        print(json.dumps({"multi_gpu": [m, n, l, q, gen], "world": world, "ok": bool(ok), "relS": relS, "err_gpu": eg, "err_oracle": eo, "orthU": orthU, "S_identical_on_all_ranks": same_S}), flush=True)
+        print(json.dumps({"multi_gpu": [m, n, l, q, gen], "world": world, "ok": bool(ok), "relS": relS, "err_gpu": eg, "err_oracle": eo, "orthU": orthU, "S_and_qr_paths_identical_on_all_ranks": same_S,
+                          "qr_paths_cholqr2_householder_so_far": [int(x) for x in cnt.tolist()]}), flush=True)
 # the ADVICE round-1 edge: shard heights straddle the wide-panel threshold 4*l (shards of 480,...,479 rows at P = 4, l = 120): every rank
 # must take the same QR branch or the collectives mismatch (pipeline.cu qr_inplace agrees on the shortest shard first)
 for l in (120,):
