@@ -282,6 +282,7 @@ def run_ours(args):
     barrier()
     eng.set_profiling(True); eng.phase_ms()
     launches0 = eng.launches
+    qr0 = eng.qr_path_counts()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -293,6 +294,7 @@ def run_ours(args):
     total_ms = e0.elapsed_time(e1)
     phases = eng.phase_ms(); eng.set_profiling(False)
     launches = eng.launches - launches0
+    qr1 = eng.qr_path_counts()
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -378,6 +380,9 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (A shard is %.1f GB)" % (rows * n * 8 / 1e9), "time_to_rank_k_ms": round(ms_per_step, 3)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "sigma_head": [float(x) for x in s_dev[:4]], "sigma_parity_vs_oracle": parity,
+            # how the 2q + 2 sketches per step were orthonormalised inside the timed region (csrc/cholqr.cu: guarded CholeskyQR2,
+            # Householder TSQR when the measured guard refuses a sketch)
+            "qr_paths": {"cholqr2": int(qr1[0] - qr0[0]), "householder_tsqr": int(qr1[1] - qr0[1])},
         }
         print(json.dumps(line), flush=True)
     eng.close()

@@ -78,7 +78,7 @@ RSVDB_API int rsvdb_qr_path_counts(const rsvdb_ctx* ctx, int64_t* cholqr2, int64
 
 /* Optional per-phase device timing (CUDA events on the context's stream).  rsvdb_phase_ms synchronises the stream,
  * writes the accumulated milliseconds per phase since the last call and clears them.
- * Phases: 0 A*X GEMMs, 1 A^T*Q GEMMs, 2 TSQR, 3 small SVD (includes its own QR), 4 collectives, 5 other, 6 host<->device copies. */
+ * Phases: 0 A*X GEMMs, 1 A^T*Q GEMMs, 2 orthonormalisations (CholeskyQR2 / Householder TSQR), 3 small SVD (includes its own QR), 4 collectives, 5 other, 6 host<->device copies. */
 #define RSVDB_NUM_PHASES 7
 RSVDB_API int rsvdb_set_profiling(rsvdb_ctx* ctx, int enabled);
 RSVDB_API int rsvdb_phase_ms(rsvdb_ctx* ctx, double* out_ms /* RSVDB_NUM_PHASES */);

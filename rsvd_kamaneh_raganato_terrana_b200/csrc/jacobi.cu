@@ -11,6 +11,7 @@
 // S >= 0 (:158-178).
 #include "dev_once.cuh"
 #include "jacobi.cuh"
+#include "ptx.cuh"
 
 #include <cfloat>
 #include <cstdlib>
@@ -59,18 +60,19 @@ k_jacobi(const double* __restrict__ W, long long ldw, int k, int transpose_in, d
   const double tol = sqrt((double)k) * (0.5 * DBL_EPSILON);
   const double tol2 = tol * tol;
   int sweep = 0; bool converged = (k < 2);
+  // one pair per half warp and step (the launch guarantees npairs <= blockDim.x / 16); the round-robin seats are advanced
+  // incrementally -- the two integer modulos per pair and step they replace were a quarter of the instruction stream
+  const int pi = grp;
   while (!converged && sweep < max_sweeps) {
     if (tid == 0) s_rot = 0;
+    int pr = (pi == 0) ? n - 1 : pi % (n - 1);
+    int qr = (pi == 0) ? 0 : (n - 1 - pi % (n - 1)) % (n - 1);
     __syncthreads();
     for (int step = 0; step < n - 1; ++step) {
       int nrot = 0;
-      for (int pi = grp; pi < ((npairs + ngrp - 1) / ngrp) * ngrp; pi += ngrp) {   // uniform trip count per half warp pair
+      {
         int p = 0, q = k;
-        if (pi < npairs) {
-          if (pi == 0) { p = n - 1; q = step; }
-          else { p = (step + pi) % (n - 1); q = (step - pi + (n - 1)) % (n - 1); }
-          if (p > q) { const int t = p; p = q; q = t; }
-        }
+        if (pi < npairs) { p = min(pr, qr); q = max(pr, qr); }
         const bool live = q < k;        // not the dummy player, not a padding pair
         double* xp = X + (size_t)(live ? p : 0) * k; double* xq = X + (size_t)(live ? q : 0) * k;
         double a = 0.0, b = 0.0, g = 0.0, vp[RPL], vq[RPL];
@@ -107,6 +109,8 @@ k_jacobi(const double* __restrict__ W, long long ldw, int k, int transpose_in, d
             }
           }
         }
+        if (pi != 0) pr = (pr + 1 == n - 1) ? 0 : pr + 1;
+        qr = (qr + 1 == n - 1) ? 0 : qr + 1;
       }
       if (nrot && hl == 0) atomicAdd(&s_rot, nrot);
       __syncthreads();
@@ -163,6 +167,27 @@ __device__ __forceinline__ void jc_store(double* p, unsigned rank, double v) {
   unsigned la = static_cast<unsigned>(__cvta_generic_to_shared(p)), ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned jc_map(const void* p, unsigned rank) {
+  unsigned la = static_cast<unsigned>(__cvta_generic_to_shared(p)), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  return ra;
+}
+// remote 8-byte store that credits 8 bytes to CTA `rank`'s copy of *bar (SASS STAS.64)
+__device__ __forceinline__ void jc_st_async(double* p, unsigned rank, double v, uint64_t* bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(jc_map(p, rank)), "l"(__double_as_longlong(v)), "r"(jc_map(bar, rank)) : "memory");
+}
+__device__ __forceinline__ void jc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
 }
 
 // RPL: rows of the CTA's slice per lane of a 16-lane group (slice rows sr = ceil(k / JC) <= 16 * RPL).
@@ -282,6 +307,189 @@ k_jacobi_cl(const double* __restrict__ W, long long ldw, int k, int transpose_in
   double* part = sig;                               // [k][JC]
   double* tot = sig + (size_t)k * JC;               // [k]
   // (the two 16-lane groups of a warp own different columns: keep the trip count uniform per warp, the shuffles are full-warp)
+  for (int j0 = 0; j0 < k; j0 += ngrp) {
+    const int j = j0 + grp; const bool on = j < k;
+    double a = 0.0;
+    if (on) for (int i = hl; i < nr; i += 16) a = fma(X[(size_t)j * sr + i], X[(size_t)j * sr + i], a);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (on && hl < JC) jc_store(part + (size_t)j * JC + rank, (unsigned)hl, a);
+  }
+  jc_sync();
+  for (int j = tid; j < k; j += blockDim.x) {
+    double a = 0.0;
+#pragma unroll
+    for (int sR = 0; sR < JC; ++sR) a += part[(size_t)j * JC + sR];
+    tot[j] = sqrt(a);
+  }
+  __syncthreads();
+  for (int j0 = 0; j0 < k; j0 += ngrp) {
+    const int j = j0 + grp; const bool on = j < k;
+    const double sj = on ? tot[j] : 0.0;
+    int r = 0;
+    if (on) for (int i = hl; i < k; i += 16) { const double si = tot[i]; r += (si > sj || (si == sj && i < j)) ? 1 : 0; }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (!on) continue;
+    const double inv = (sj > 0.0) ? 1.0 / sj : 0.0;
+    if (rank == 0 && hl == 0) So[r] = sj;
+    for (int i = hl; i < nr; i += 16) {
+      const int gi = r0 + i;
+      Uo[(size_t)r * ldu + gi] = (sj > 0.0) ? X[(size_t)j * sr + i] * inv : (gi == j ? 1.0 : 0.0);
+      Zo[(size_t)r * ldz + gi] = Z[(size_t)j * sr + i];
+    }
+  }
+  if (rank == 0 && tid == 0 && info) { info[0] = converged ? sweep : -sweep; info[1] = s_total; }
+  jc_sync();                                        // peers may still be reading this CTA's shared memory
+}
+
+// Round-2 revision of the cluster kernel's step.  ncu on the version above: issue slots 50 % busy, barrier 3.8 + membar 1.9 stall
+// cycles per issue -- every step paid one hardware cluster barrier (4096 threads, release/acquire fences over all memory) plus ~8
+// integer modulos per thread for the round-robin pairing.  Here
+//  * a pair's three partial inner products travel with st.async ... mbarrier::complete_tx to one mbarrier PER PAIR AND BUFFER on
+//    every CTA, and only the half warp that owns the pair waits for it (no cluster barrier in the sweep at all; the block barrier
+//    at the end of a step, which hands the rotated columns to their next owners, stays);
+//  * the pairing is advanced incrementally (p, q -> p + 1, q + 1 mod n - 1) and kept in registers across both halves of a step.
+// Buffer reuse is safe with two buffers: a CTA can pass the wait of step s + 1 only after every peer has sent its step-(s + 1)
+// partials, i.e. after that peer's half warp has finished reading step s, so writes of step s + 2 never meet reads of step s.
+template <int RPL, int ROUNDS>
+__global__ void __cluster_dims__(JC, 1, 1) __launch_bounds__(1024, 1)
+k_jacobi_cl2(const double* __restrict__ W, long long ldw, int k, int transpose_in, double* __restrict__ Uo, long long ldu,
+             double* __restrict__ So, double* __restrict__ Zo, long long ldz, int max_sweeps, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  __shared__ int s_rot;
+  __shared__ int s_total;
+  const unsigned rank = jc_rank();
+  const int sr = (k + JC - 1) / JC;                 // slice rows
+  const int r0 = (int)rank * sr;
+  const int nr = max(0, min(sr, k - r0));
+  const int n = (k + 1) & ~1, npairs = n >> 1;
+  double* X = sm;                                   // k columns of sr rows
+  double* Z = X + (size_t)k * sr;
+  double* xch = Z + (size_t)k * sr;                 // [2][npairs][JC][4]
+  double* sig = xch + 2 * (size_t)npairs * JC * 4;  // [k][JC] partial squared norms, then [k] totals behind it
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sig + (size_t)k * JC + k);   // [2][npairs]
+  const int tid = threadIdx.x, hl = tid & 15, grp = tid >> 4, ngrp = blockDim.x >> 4;
+  const unsigned hmask = (tid & 16) ? 0xffff0000u : 0x0000ffffu;   // the two half warps of a warp may own a live and a padding pair
+
+  for (int e = tid; e < k * sr; e += blockDim.x) {
+    const int i = e % sr, j = e / sr, gi = r0 + i;
+    double x = 0.0;
+    if (i < nr) x = transpose_in ? W[(size_t)gi * ldw + j] : W[(size_t)j * ldw + gi];
+    X[e] = x;
+    Z[e] = (i < nr && gi == j) ? 1.0 : 0.0;
+  }
+  for (int e = tid; e < 2 * npairs; e += blockDim.x) mbar_init(&bar[e], 1);
+  if (tid == 0) s_total = 0;
+  fence_mbar_init();
+  __syncthreads();
+  constexpr uint32_t TX = JC * 3 * sizeof(double);  // three doubles from every CTA of the cluster (this one included)
+#pragma unroll
+  for (int rd = 0; rd < ROUNDS; ++rd) {
+    const int pi = grp + rd * ngrp;
+    if (pi < npairs && hl == 0) { mbar_expect_tx(&bar[pi], TX); mbar_expect_tx(&bar[npairs + pi], TX); }
+  }
+  jc_sync();                                        // every CTA's barriers exist and are armed before the first remote store
+
+  const double tol = sqrt((double)k) * (0.5 * DBL_EPSILON);
+  const double tol2 = tol * tol;
+  uint32_t phase = 0;                               // bit b: parity to wait for on buffer b
+  int sweep = 0, buf = 0; bool converged = (k < 2);
+  while (!converged && sweep < max_sweeps) {
+    if (tid == 0) s_rot = 0;
+    int pr[ROUNDS], qr[ROUNDS];                     // raw round-robin seats of this half warp's pairs at step 0
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      const int pi = grp + rd * ngrp;
+      pr[rd] = (pi == 0) ? n - 1 : pi % (n - 1);
+      qr[rd] = (pi == 0) ? 0 : (n - 1 - pi % (n - 1)) % (n - 1);
+    }
+    __syncthreads();
+    for (int step = 0; step < n - 1; ++step) {
+      int pp[ROUNDS], qq[ROUNDS];
+      // (1) partial inner products of every pair over this CTA's rows -> all CTAs
+#pragma unroll
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int pi = grp + rd * ngrp;
+        const int p = min(pr[rd], qr[rd]), q = max(pr[rd], qr[rd]);
+        pp[rd] = p; qq[rd] = q;
+        if (pi < npairs) {
+          const bool live = q < k;
+          const double* xp = X + (size_t)(live ? p : 0) * sr; const double* xq = X + (size_t)(live ? q : 0) * sr;
+          double a = 0.0, b = 0.0, g = 0.0;
+#pragma unroll
+          for (int ii = 0; ii < RPL; ++ii) {
+            const int i = hl + 16 * ii;
+            const bool on = live && i < nr;
+            const double vp = on ? xp[i] : 0.0, vq = on ? xq[i] : 0.0;
+            a = fma(vp, vp, a); b = fma(vq, vq, b); g = fma(vp, vq, g);
+          }
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(hmask, a, o); b += __shfl_xor_sync(hmask, b, o); g += __shfl_xor_sync(hmask, g, o);
+          }
+          if (hl < 3 * JC) {                          // lanes 0..11: value hl % 3 to CTA hl / 3
+            const double v = (hl % 3 == 0) ? a : ((hl % 3 == 1) ? b : g);
+            jc_st_async(xch + (((size_t)buf * npairs + pi) * JC + rank) * 4 + (hl % 3), (unsigned)(hl / 3), v, &bar[buf * npairs + pi]);
+          }
+        }
+      }
+      // (2) every CTA takes the same decision and rotates its rows
+      int nrot = 0;
+#pragma unroll
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int pi = grp + rd * ngrp;
+        const int p = pp[rd], q = qq[rd];
+        if (pi < npairs) {
+          jc_mbar_wait(&bar[buf * npairs + pi], (phase >> buf) & 1u);
+          const double* xx = xch + ((size_t)buf * npairs + pi) * JC * 4;
+          double a = 0.0, b = 0.0, g = 0.0;
+#pragma unroll
+          for (int sR = 0; sR < JC; ++sR) { a += xx[sR * 4 + 0]; b += xx[sR * 4 + 1]; g += xx[sR * 4 + 2]; }
+          __syncwarp(hmask);     // all 16 lanes hold the sums before the barrier is re-armed
+          if (hl == 0) mbar_expect_tx(&bar[buf * npairs + pi], TX);     // its next use is two steps away
+          if (q < k && g * g > tol2 * (a * b) && fabs(g) > DBL_MIN) {
+            ++nrot;
+            const double d = b - a;
+            const double n2 = fma(d, d, 4.0 * g * g);
+            const double ir = rsqrt(n2);
+            const double c2 = fma(0.5 * fabs(d), ir, 0.5);
+            const double ic = rsqrt(c2);
+            const double c = c2 * ic;
+            const double s = ((d >= 0.0) ? g : -g) * ir * ic;
+            double* xp = X + (size_t)p * sr; double* xq = X + (size_t)q * sr;
+            double* zp = Z + (size_t)p * sr; double* zq = Z + (size_t)q * sr;
+#pragma unroll
+            for (int ii = 0; ii < RPL; ++ii) {
+              const int i = hl + 16 * ii;
+              if (i < nr) {
+                const double x1 = xp[i], x2 = xq[i];
+                xp[i] = c * x1 - s * x2; xq[i] = s * x1 + c * x2;
+                const double z1 = zp[i], z2 = zq[i];
+                zp[i] = c * z1 - s * z2; zq[i] = s * z1 + c * z2;
+              }
+            }
+          }
+        }
+        // next step's seats: everybody but seat n - 1 moves up by one
+        if (pi != 0) { pr[rd] = (pr[rd] + 1 == n - 1) ? 0 : pr[rd] + 1; }
+        qr[rd] = (qr[rd] + 1 == n - 1) ? 0 : qr[rd] + 1;
+      }
+      if (nrot && hl == 0) atomicAdd(&s_rot, nrot);
+      phase ^= (1u << buf);
+      __syncthreads();
+      buf ^= 1;
+    }
+    ++sweep;
+    converged = (s_rot == 0);                       // identical on every CTA: same sums, same decisions
+    if (tid == 0) s_total += s_rot;
+    __syncthreads();
+  }
+
+  // singular values: column norms summed over the cluster
+  double* part = sig;                               // [k][JC]
+  double* tot = sig + (size_t)k * JC;               // [k]
+  jc_sync();                                        // nobody is still inside the sweeps when the remote stores below land
   for (int j0 = 0; j0 < k; j0 += ngrp) {
     const int j = j0 + grp; const bool on = j < k;
     double a = 0.0;
@@ -446,14 +654,19 @@ cudaError_t jacobi_svd_square(GemmWorkspace& ws, cudaStream_t st, const double* 
     const int sr = (k + JC - 1) / JC, npairs = ((k + 1) & ~1) >> 1;
     const size_t cl_smem = (2 * (size_t)k * sr + 2 * (size_t)npairs * JC * 4 + (size_t)k * JC + k) * sizeof(double);
     static const bool cl_off = getenv("RSVDB_JACOBI_NO_CLUSTER") != nullptr;
+    static const bool cl_old = getenv("RSVDB_JACOBI_CL_OLD") != nullptr;       // the barrier.cluster-per-step version, kept for A/B timing
     // measured: the per-step cluster barrier outweighs the bandwidth gain below k ~ 80 (k = 50: 0.99 vs 0.88 ms, k = 100: 1.18 vs 1.40 ms)
-    if (!cl_off && k >= 80 && cl_smem <= 220 * 1024 && sr <= 64) {
+    if (!cl_off && k >= 80 && cl_smem + 2 * npairs * 8 <= 220 * 1024 && sr <= 64 && npairs <= 128) {
       const int rplc = (sr + 15) / 16;
 #define JCL(R)                                                                                                         \
       { static DevOnce attr;                                                                                           \
         if (!attr.get()) { cudaError_t e = cudaFuncSetAttribute(k_jacobi_cl<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
+                     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_jacobi_cl2<R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
+                     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_jacobi_cl2<R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
                      if (e != cudaSuccess) return e; attr.set(); }                                                    \
-        k_jacobi_cl<R><<<JC, 1024, cl_smem, st>>>(W, ldw, k, transpose_in, U, ldu, S, Z, ldz, 60, d_info); }
+        if (cl_old) k_jacobi_cl<R><<<JC, 1024, cl_smem, st>>>(W, ldw, k, transpose_in, U, ldu, S, Z, ldz, 60, d_info);  \
+        else if (npairs <= 64) k_jacobi_cl2<R, 1><<<JC, 1024, cl_smem + 2 * npairs * 8, st>>>(W, ldw, k, transpose_in, U, ldu, S, Z, ldz, 60, d_info); \
+        else k_jacobi_cl2<R, 2><<<JC, 1024, cl_smem + 2 * npairs * 8, st>>>(W, ldw, k, transpose_in, U, ldu, S, Z, ldz, 60, d_info); }
       if (rplc <= 1) JCL(1) else if (rplc <= 2) JCL(2) else if (rplc <= 3) JCL(3) else JCL(4)
 #undef JCL
       if (launches) ++*launches;

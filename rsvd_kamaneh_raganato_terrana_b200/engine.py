@@ -99,7 +99,7 @@ class Engine:
     def phase_ms(self) -> dict:
         out = (ctypes.c_double * 7)()
         self._check(self.lib.rsvdb_phase_ms(self.h, out))
-        names = ["gemm_an", "gemm_at", "tsqr", "small_svd", "comm", "other", "copy"]
+        names = ["gemm_an", "gemm_at", "qr", "small_svd", "comm", "other", "copy"]
         return dict(zip(names, [float(x) for x in out]))
 
     def last_svd_info(self):
