@@ -221,6 +221,11 @@ int orthonormalize(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bo
     if (done) { ++c->qr_fast; return 0; }
     c->chol_failed = true;              // ill-conditioned or rank-deficient sketch: the rest of this factorisation stays on Householder
   }
+  if (l > CHOL_MAX_L && policy == 0 && !c->wide_fast) {
+    // wider than the Cholesky kernel: block Gram-Schmidt over <= 104-column blocks (qr_wide), each block through this function
+    struct Scope { rsvdb_ctx* c; Scope(rsvdb_ctx* x) : c(x) { c->wide_fast = true; } ~Scope() { c->wide_fast = false; } } scope(c);
+    return qr_inplace(c, Y, rows, l, ldy, sharded, R);
+  }
   ++c->qr_householder;
   return qr_inplace(c, Y, rows, l, ldy, sharded, R);
 }

@@ -30,6 +30,7 @@ struct rsvdb_ctx {
   int qr_policy = -1;               // -1: environment default (RSVDB_CHOLQR), 0: guarded CholeskyQR2 then Householder, 1: Householder only
   bool chol_failed = false;         // the guard refused a sketch of the factorisation in flight: stay on Householder for the rest of it
   bool in_rsvd = false;
+  bool wide_fast = false;           // qr_wide was entered from the pipeline's orthonormalize: its blocks may take the fast path
   int64_t qr_fast = 0, qr_householder = 0;   // sketches orthonormalised by either path (rsvdb_qr_path_counts)
   int64_t launches = 0;
   std::string err;

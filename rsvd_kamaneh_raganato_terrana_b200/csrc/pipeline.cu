@@ -93,6 +93,11 @@ __global__ void k_place(double* __restrict__ R, int ldr, int r0, int c0, const d
 // dependent on its predecessors (rank-deficient sketches); R is assembled from the projection coefficients.
 // All products run on the DMMA GEMM kernels; with row shards the coefficients are all-reduced.
 static int qr_wide(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bool sharded, const double** Rout) {
+  // a block (<= 104 columns, projected against its predecessors) is factored like any sketch of the pipeline: guarded CholeskyQR2
+  // when the caller is the pipeline's orthonormalize (c->wide_fast), Householder TSQR for the QR class
+  auto block_qr = [&](double* Yk, int ck, const double** Rk) -> int {
+    return c->wide_fast ? orthonormalize(c, Yk, rows, ck, ldy, sharded, Rk) : qr_inplace(c, Yk, rows, ck, ldy, sharded, Rk);
+  };
   const int nblk = (l + QR_WIDE_BLOCK - 1) / QR_WIDE_BLOCK;
   const int bw = (((l + nblk - 1) / nblk) + 7) & ~7;
   const size_t d_R = (size_t)l * l, d_W = (size_t)l * bw, d_P = (size_t)std::max<int64_t>(rows, 1) * bw, d_s = (size_t)bw * bw;
@@ -115,7 +120,7 @@ static int qr_wide(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bo
     double* Yk = Y + (size_t)col0 * ldy;
     const double* Rk = nullptr;
     if (col0 == 0) {
-      RSVDB_TRY(qr_inplace(c, Yk, rows, ck, ldy, sharded, &Rk));
+      RSVDB_TRY(block_qr(Yk, ck, &Rk));
       k_place<<<(ck * ck + 255) / 256, 256, 0, st>>>(R, l, 0, 0, Rk, ck, ck, ck, 0); ++nl;
       continue;
     }
@@ -125,11 +130,11 @@ static int qr_wide(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy, bo
     RSVDB_TRY(project(Yk, col0, ck, Wb));
     k_place<<<(col0 * ck + 255) / 256, 256, 0, st>>>(R, l, 0, col0, Wb, col0, col0, ck, 1); ++nl;
     // Y_k'' = Q1 R1
-    RSVDB_TRY(qr_inplace(c, Yk, rows, ck, ldy, sharded, &Rk));
+    RSVDB_TRY(block_qr(Yk, ck, &Rk));
     RSVDB_CUDA(c, cudaMemcpyAsync(R1, Rk, (size_t)ck * ck * sizeof(double), cudaMemcpyDeviceToDevice, st));
     // Q1 = Qp W_c + Q2 R2                     (re-orthogonalise the block against its predecessors)
     RSVDB_TRY(project(Yk, col0, ck, W2));
-    RSVDB_TRY(qr_inplace(c, Yk, rows, ck, ldy, sharded, &Rk));
+    RSVDB_TRY(block_qr(Yk, ck, &Rk));
     RSVDB_CUDA(c, cudaMemcpyAsync(R2, Rk, (size_t)ck * ck * sizeof(double), cudaMemcpyDeviceToDevice, st));
     // R[0:col0, blk] += W_c R1 ;  R[blk, blk] = R2 R1
     RSVDB_CUDA(c, gemm_generic(st, 0, 0, col0, ck, ck, 1.0, W2, col0, R1, ck, 1.0, R + (size_t)col0 * l, l)); ++nl;

@@ -1489,7 +1489,8 @@ def _sketch(torch, dev, rows, l, kind, seed=0):
     (12345, 37, "kappa3", 0), (20000, 100, "kappa6", 0),                        # well inside the guard
     (20000, 100, "kappa10", 1), (20000, 64, "kappa14", 1),                      # the measured ||Q1^T Q1 - I|| refuses them
     (5000, 50, "rank5", 1), (3000, 64, "zero_col", 1), (2049, 100, "rank5", 1), # Cholesky breakdown
-    (30000, 8, "randn", 1), (300, 100, "randn", 1), (30000, 129, "randn", 1),   # outside the fast path's range by construction
+    (30000, 8, "randn", 1), (300, 100, "randn", 1),                             # outside the fast path's range by construction
+    (30000, 129, "randn", 2), (20000, 200, "randn", 2), (6000, 150, "rank5", 2), # wider than the Cholesky kernel: block Gram-Schmidt, each block guarded
 ])
 def test_orthonormalize_guarded_cholqr2_and_householder_fallback(engine, rows, l, kind, path):
     import torch
@@ -1501,7 +1502,10 @@ def test_orthonormalize_guarded_cholqr2_and_householder_fallback(engine, rows, l
         f0, h0 = engine.qr_path_counts()
         took = engine.orthonormalize_dev(Y.data_ptr(), rows, l, rows, False, R.data_ptr()); torch.cuda.synchronize()
         f1, h1 = engine.qr_path_counts()
-        assert took == path and (f1 - f0, h1 - h0) == ((1, 0) if path == 0 else (0, 1))
+        if path == 2:
+            assert (f1 - f0) + (h1 - h0) >= 3 and (kind != "randn" or (took == 0 and h1 == h0))
+        else:
+            assert took == path and (f1 - f0, h1 - h0) == ((1, 0) if path == 0 else (0, 1))
         Q, Rm = Y.T, R.T
         eye = torch.eye(l, dtype=torch.float64, device=dev)
         assert (Q.T @ Q - eye).norm().item() <= 1e-12                                     # tolerance: 1e-10 (ORTH_TOL) with margin
@@ -1512,7 +1516,9 @@ def test_orthonormalize_guarded_cholqr2_and_householder_fallback(engine, rows, l
         # same basis as the Householder-only policy: the projector onto the numerically non-degenerate part agrees
         engine.set_qr_policy(True)
         Yh = Y0.clone()
+        h2 = engine.qr_path_counts()
         assert engine.orthonormalize_dev(Yh.data_ptr(), rows, l, rows, False, None) == 1; torch.cuda.synchronize()
+        assert engine.qr_path_counts()[0] == h2[0]                                        # no CholeskyQR2 anywhere under policy 1
         if kind in ("randn", "kappa3", "kappa6"):
             Qh = Yh.T
             assert (Q - Qh @ (Qh.T @ Q)).norm().item() <= 1e-9 * (10.0 ** (6 if kind == "kappa6" else 0))

@@ -19,7 +19,7 @@ E.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
 E.set_stream(torch.cuda.current_stream().cuda_stream)
 ok_all = True
 for (m, n, l, q, gen) in [(3001, 400, 32, 2, "pod"), (20000, 1500, 100, 2, "gauss"), (1000, 300, 16, 1, "rank2"), (50000, 2000, 64, 2, "pod"),
-                          (3000, 500, 120, 1, "gauss"), (2001, 640, 101, 2, "gauss")]:     # wide / odd sketches: block Gram-Schmidt TSQR over shards
+                          (3000, 500, 120, 1, "gauss"), (2001, 640, 101, 2, "gauss"), (12000, 700, 160, 1, "gauss")]:     # wide / odd sketches: block Gram-Schmidt TSQR over shards
     rng = np.random.default_rng(42)
     if gen == "pod": A = W.c4_pod(m, n)
     elif gen == "rank2": A = np.asfortranarray(np.outer(rng.standard_normal(m), rng.standard_normal(n)) + np.outer(rng.standard_normal(m), rng.standard_normal(n)))

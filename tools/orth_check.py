@@ -62,6 +62,6 @@ for rows, l, kind, expect in [
         (100000, 20, "randn", 0), (4096, 50, "randn", 0), (256, 100, "randn", 1), (100, 100, "randn", 1), (777, 33, "randn", 0),
         (12345, 37, "kappa3", 0), (20000, 100, "kappa6", 0), (20000, 100, "kappa7", None), (20000, 100, "kappa8", None),
         (20000, 100, "kappa10", 1), (20000, 100, "kappa14", 1), (5000, 50, "rank5", 1), (3000, 64, "zero_col", 1), (2049, 100, "rank5", 1),
-        (20001, 101, "randn", 0), (9999, 112, "randn", 0), (30000, 113, "randn", 0), (30000, 128, "randn", 0), (30000, 129, "randn", 1), (3000, 96, "randn", 0), (3000, 97, "randn", 0), (3000, 32, "randn", 0), (3000, 65, "randn", 0), (30001, 8, "randn", 1), (5000, 1, "randn", 1), (30001, 16, "randn", 0)]:
+        (20001, 101, "randn", 0), (9999, 112, "randn", 0), (30000, 113, "randn", 0), (30000, 128, "randn", 0), (30000, 129, "randn", None), (50000, 200, "randn", None), (8000, 256, "kappa3", None), (6000, 150, "rank5", None), (3000, 96, "randn", 0), (3000, 97, "randn", 0), (3000, 32, "randn", 0), (3000, 65, "randn", 0), (30001, 8, "randn", 1), (5000, 1, "randn", 1), (30001, 16, "randn", 0)]:
     ok &= run(rows, l, kind, expect)
 print(json.dumps({"all_ok": bool(ok), "counts": E.qr_path_counts()}))
