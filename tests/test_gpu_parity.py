@@ -423,8 +423,9 @@ def test_pageable_host_matrices_upload_through_the_pinned_ring(engine, oracle):
     assert np.linalg.norm(Q.T @ Q - np.eye(l)) <= ORTH_TOL and oracle.subspace_sin_theta(Qo, Q) <= SIN_TOL
     gbs = A.nbytes / dt * 1e-9
     print(f"pageable upload + one pass + QR of {A.nbytes / 1e9:.2f} GB: {dt * 1e3:.1f} ms = {gbs:.1f} GB/s end to end")
-    assert gbs > 1.0      # measured 15-25 GB/s on an idle box (round 1: ~11 through the bounce buffer); the pod's hosts are shared, so only a
-                          # collapse is asserted here -- the number itself is printed and recorded in profiles/r02_apps_bench.log
+    assert gbs > 0.2      # measured 15-25 GB/s alone on the box (round 1: ~11 through the bounce buffer), but 1.4 and 2.1 GB/s were seen once each
+                          # inside full-suite runs on the shared hosts (same code: 17.5 GB/s a minute later), so this is a liveness bound, not a
+                          # performance gate -- the number is printed and recorded in profiles/ (r02_pytest_gpu*.log, r02_apps_bench.log)
     # a matrix whose columns are longer than one 64 MB chunk (rows > 8M): the stager tiles the rows as well
     m2, n2 = 9_000_001, 3
     B = np.asfortranarray(rng.standard_normal((m2, n2)))
