@@ -241,7 +241,7 @@ int rsvdb_orthonormalize_dev(rsvdb_ctx* c, double* dY, int64_t rows, int l, int6
   const double* R = nullptr;
   const int64_t fast0 = c->qr_fast;
   c->chol_failed = false;
-  RSVDB_TRY(orthonormalize(c, dY, rows, l, ldy, sharded != 0, &R));
+  RSVDB_TRY(orthonormalize(c, dY, rows, l, ldy, sharded != 0, dR ? &R : nullptr));   // without R the second round may take its first-order form
   if (dR) RSVDB_CUDA(c, cudaMemcpyAsync(dR, R, (size_t)l * l * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   if (path) *path = (c->qr_fast > fast0) ? 0 : 1;
   return RSVDB_OK;

@@ -11,7 +11,8 @@
 // in a quarter of the time -- PROVIDED Y is not too ill-conditioned: the first round leaves ||Q1^T Q1 - I|| ~ kappa(Y)^2 u,
 // and the second round restores orthogonality to O(u) only if that is well below 1 (Yamamoto et al. 2015).  The guard is
 // measured, not estimated: the second Gram matrix IS Q1^T Q1, its distance from I is computed while it is loaded, and the
-// host reads it (one 32-byte read-back per QR) before Y is overwritten.  A Cholesky breakdown (non-positive pivot: rank-
+// host reads it (one 32-byte read-back per QR) before Y is overwritten.  When that distance is below 1e-9 -- the usual case --
+// and no R is wanted, round 2 needs no Cholesky at all: X = I - E/2 is (I + E)^(-1/2) to 4e-19.  A Cholesky breakdown (non-positive pivot: rank-
 // deficient sketches such as the reference's configs 1 and 4) or a distance above CHOL_DEV_TOL leaves Y untouched and the
 // caller runs the Householder TSQR exactly as before.  Nothing is ever computed on the CPU.
 #include "pipeline.cuh"
@@ -28,6 +29,7 @@ namespace {
 constexpr int CH_THREADS = 1024;
 constexpr int CHOL_MIN_L = 16;
 constexpr int CHOL_MAX_L = 128;            // 32 x 32 threads own up to 4 x 4 entries of the l x l work matrix each
+constexpr double CHOL_FIRST_ORDER_TOL = 1e-9;  // ||Q1^T Q1 - I||_F below which round 2 uses X = I - E/2 instead of a Cholesky
 constexpr double CHOL_DEV_TOL = 0.05;      // ||Q1^T Q1 - I||_F accepted before the second round (theory: <= 5/64)
 
 // G (l x l, symmetric, column-major ldg) = L L^T.  Right-looking; the same eliminations run on an identity, so L^-1 is
@@ -46,7 +48,7 @@ constexpr double CHOL_DEV_TOL = 0.05;      // ||Q1^T Q1 - I||_F accepted before 
 template <int NT>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 k_chol_inv(const double* __restrict__ G, int ldg, int l, double* __restrict__ X, int ldx, double* __restrict__ R, int ldr,
-           double* __restrict__ info) {
+           double* __restrict__ info, int first_order_ok) {
   __shared__ double vec[2][32 * NT];
   __shared__ double piv[32 * NT], sinv[32 * NT];          // pivots and their rsqrt (computed once, by the owner)
   __shared__ double s_red[32];
@@ -70,6 +72,29 @@ k_chol_inv(const double* __restrict__ G, int ldg, int l, double* __restrict__ X,
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dev += __shfl_xor_sync(0xffffffffu, dev, o);
   if (tx == 0) s_red[ty] = dev;
+  __syncthreads();
+  if (first_order_ok) {
+    // Second round on a sketch that is already orthonormal to ||E||_F <= 1e-9 (G = I + E; the usual case: kappa(Y)^2 u is far
+    // below that): X = I - E/2 is G^(-1/2) up to 3/8 E^2 <= 4e-19, so the l sequential pivots are skipped.  X is symmetric
+    // instead of triangular, which is why the caller allows this only when it does not ask for R.
+    double t = 0.0;
+    for (int w = 0; w < CH_THREADS / 32; ++w) t += s_red[w];          // same order on every thread: uniform decision
+    if (t <= CHOL_FIRST_ORDER_TOL * CHOL_FIRST_ORDER_TOL) {
+#pragma unroll
+      for (int a = 0; a < NT; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          const int i = ty + 32 * a, c = tx + 32 * b;
+          if (i < l && c <= i) {
+            const double x = (i == c) ? 1.0 - 0.5 * (m[a][b] - 1.0) : -0.5 * m[a][b];
+            X[(size_t)i * ldx + c] = x;
+            if (i != c) X[(size_t)c * ldx + i] = x;
+          }
+        }
+      if (tid == 0) { info[1] = t; info[0] = 0.0; }
+      return;
+    }
+  }
 
   int bad = 0;
 #pragma unroll
@@ -167,17 +192,17 @@ static int cholqr2_try(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy
   double* G = T + (size_t)ldt * l; double* X1 = G + sq; double* X2 = X1 + sq;
   double* R1 = X2 + sq; double* R2 = R1 + sq; double* R = R2 + sq; double* info = R + sq;
   if (!c->chol_host) RSVDB_CUDA(c, cudaMallocHost(&c->chol_host, 8 * sizeof(double)));
-  auto chol = [&](const double* Gm, double* Xk, double* Rk, double* inf) {
-    if (l <= 32) k_chol_inv<1><<<1, CH_THREADS, 0, st>>>(Gm, ldl, l, Xk, ldl, Rk, ldl, inf);
-    else if (l <= 64) k_chol_inv<2><<<1, CH_THREADS, 0, st>>>(Gm, ldl, l, Xk, ldl, Rk, ldl, inf);
-    else if (l <= 96) k_chol_inv<3><<<1, CH_THREADS, 0, st>>>(Gm, ldl, l, Xk, ldl, Rk, ldl, inf);
-    else k_chol_inv<4><<<1, CH_THREADS, 0, st>>>(Gm, ldl, l, Xk, ldl, Rk, ldl, inf);
+  auto chol = [&](const double* Gm, double* Xk, double* Rk, double* inf, int fo) {
+    if (l <= 32) k_chol_inv<1><<<1, CH_THREADS, 0, st>>>(Gm, ldl, l, Xk, ldl, Rk, ldl, inf, fo);
+    else if (l <= 64) k_chol_inv<2><<<1, CH_THREADS, 0, st>>>(Gm, ldl, l, Xk, ldl, Rk, ldl, inf, fo);
+    else if (l <= 96) k_chol_inv<3><<<1, CH_THREADS, 0, st>>>(Gm, ldl, l, Xk, ldl, Rk, ldl, inf, fo);
+    else k_chol_inv<4><<<1, CH_THREADS, 0, st>>>(Gm, ldl, l, Xk, ldl, Rk, ldl, inf, fo);
   };
   int nl = 0;
   auto round = [&](const double* src, int64_t lds, double* dst, int64_t ldd, double* Xk, double* Rk, double* inf) -> int {
     RSVDB_CUDA(c, gemm_at(c->gemm_ws, st, c->nsm, src, rows, l, lds, src, lds, l, G, ldl, 0, &nl));       // G = src^T src
     if (dist) { PhaseTimer pc(c, PH_COMM); RSVDB_TRY(comm_allreduce_sum(c, G, sq)); }
-    chol(G, Xk, Rk, inf); ++nl;
+    chol(G, Xk, Rk, inf, 0); ++nl;
     RSVDB_CUDA(c, cudaGetLastError());
     RSVDB_CUDA(c, gemm_an(c->gemm_ws, st, c->nsm, src, rows, l, lds, Xk, ldl, l, dst, ldd, &nl));          // dst = src X
     return 0;
@@ -186,7 +211,7 @@ static int cholqr2_try(rsvdb_ctx* c, double* Y, int64_t rows, int l, int64_t ldy
   RSVDB_TRY(round(Y, ldy, T, ldt, X1, Rout ? R1 : nullptr, info));
   RSVDB_CUDA(c, gemm_at(c->gemm_ws, st, c->nsm, T, rows, l, ldt, T, ldt, l, G, ldl, 0, &nl));
   if (dist) { PhaseTimer pc(c, PH_COMM); RSVDB_TRY(comm_allreduce_sum(c, G, sq)); }
-  chol(G, X2, Rout ? R2 : nullptr, info + 2); ++nl;
+  chol(G, X2, Rout ? R2 : nullptr, info + 2, Rout ? 0 : 1); ++nl;                     // no R wanted: X2 may be the symmetric I - E/2
   RSVDB_CUDA(c, cudaGetLastError());
   RSVDB_CUDA(c, cudaMemcpyAsync(c->chol_host, info, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
   RSVDB_CUDA(c, cudaStreamSynchronize(st));
