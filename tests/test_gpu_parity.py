@@ -1514,6 +1514,13 @@ def test_orthonormalize_guarded_cholqr2_and_householder_fallback(engine, rows, l
         assert torch.tril(Rm, -1).abs().max().item() == 0.0
         if path == 0:
             assert bool((torch.diagonal(Rm) > 0).all().item())
+        if path == 0:
+            # without R the second round may use its first-order form (X = I - E/2 when ||Q1^T Q1 - I||_F <= 1e-9): same accuracy
+            Yn = Y0.clone()
+            assert engine.orthonormalize_dev(Yn.data_ptr(), rows, l, rows, False, None) == 0; torch.cuda.synchronize()
+            Qn = Yn.T
+            assert (Qn.T @ Qn - eye).norm().item() <= 1e-12
+            assert (Qn - Q @ (Q.T @ Qn)).norm().item() <= 1e-9 * (10.0 ** (6 if kind == "kappa6" else (3 if kind == "kappa3" else 0)))
         # same basis as the Householder-only policy: the projector onto the numerically non-degenerate part agrees
         engine.set_qr_policy(True)
         Yh = Y0.clone()
