@@ -146,6 +146,28 @@ def test_sharded_guarded_cholqr2_two_gloo_ranks(tmp_path, oracle, rank_def):
     assert oracle.subspace_sin_theta(Uo[:, :r], U[:, :r]) < 1e-8
 
 
+def test_chol_inv_model_matches_lapack():
+    """tests/sharded_model._chol_inv restates csrc/cholqr.cu k_chol_inv (right-looking Cholesky that builds L^-1 alongside L and reports
+    the first non-positive pivot and ||G - I||_F^2): check it against LAPACK so that the gloo model above rests on something."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import sharded_model
+    rng = np.random.default_rng(3)
+    for l in (1, 2, 7, 33, 100):
+        Y = rng.standard_normal((4 * l + 5, l))
+        G = Y.T @ Y
+        bad, dev2, X, R = sharded_model._chol_inv(G)
+        assert bad == 0
+        assert np.allclose(dev2, np.linalg.norm(G - np.eye(l)) ** 2, rtol=1e-12)
+        assert np.allclose(R, np.linalg.cholesky(G).T, rtol=1e-10, atol=1e-12) and np.all(np.tril(R, -1) == 0)
+        assert np.linalg.norm(X @ R - np.eye(l)) < 1e-10 * np.linalg.cond(R) and np.all(np.tril(X, -1) == 0)
+        assert np.linalg.norm(X.T @ G @ X - np.eye(l)) < 1e-9
+    Y = rng.standard_normal((50, 6)); Y[:, 4] = Y[:, 1] - 2.0 * Y[:, 3]          # exactly dependent column: breakdown at or after it
+    bad, _, X, R = sharded_model._chol_inv(Y.T @ Y)
+    assert bad == 0 or bad >= 5
+    Z = np.zeros((10, 3))
+    assert sharded_model._chol_inv(Z.T @ Z)[0] == 1
+
+
 def _rpca_worker(rank, world, port, m, n, l, q, out_dir):
     import torch
     import torch.distributed as dist
